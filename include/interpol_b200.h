@@ -1,0 +1,173 @@
+/*
+ * interpol_b200.h -- C ABI of the B200-native spline sampling engine.
+ *
+ * This is the drop-in boundary for ONE hot path of balbasty/torch-interpol:
+ * the non-differentiable forward/backward building blocks that
+ * interpol/autograd.py calls in interpol/pushpull.py and interpol/coeff.py.
+ * Every entry point below names the reference function it replaces
+ * (file:line relative to the reference tree).  Plain pointers and sizes only:
+ * no torch types cross this boundary.  All pointers are DEVICE pointers on
+ * `device` unless stated otherwise; work is enqueued on `stream`
+ * (a cudaStream_t passed as void*) and the call returns without
+ * synchronising.  The library never allocates or frees device memory: outputs
+ * and scratch are owned by the caller.
+ *
+ * Layouts: volumes are (B, C, X[, Y[, Z]]), grids are
+ * (B, X[, Y[, Z]], D) in voxel units with component d indexing spatial axis d,
+ * last spatial axis fastest in the dense case.  Inputs may be arbitrarily
+ * strided (element strides, 0 allowed for broadcast batch / channel axes);
+ * outputs are always dense C-contiguous.
+ *
+ * Return value: 0 on success, a negative IB200_ERR_* code otherwise
+ * (IB200_ERR_CUDA - cudaError_t for CUDA runtime failures).  No exception ever
+ * crosses the boundary; the Python host maps codes to the reference's
+ * exception classes (ValueError / NotImplementedError / RuntimeError).
+ */
+#ifndef INTERPOL_B200_H
+#define INTERPOL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define IB200_API __attribute__((visibility("default")))
+#else
+#define IB200_API
+#endif
+
+/* dtype codes (storage type; arithmetic is f32 for F16/BF16/F32, f64 for F64) */
+enum { IB200_F16 = 0, IB200_F32 = 1, IB200_F64 = 2, IB200_BF16 = 3 };
+
+/* boundary codes == interpol/bounds.py:8-15 (BoundType) */
+enum {
+    IB200_BOUND_ZERO = 0, IB200_BOUND_REPLICATE = 1, IB200_BOUND_DCT1 = 2,
+    IB200_BOUND_DCT2 = 3, IB200_BOUND_DST1 = 4, IB200_BOUND_DST2 = 5,
+    IB200_BOUND_DFT = 6
+};
+
+/* extrapolate codes == interpol/bounds.py:18-21 (ExtrapolateType) */
+enum { IB200_EXTRAPOLATE_NO = 0, IB200_EXTRAPOLATE_YES = 1, IB200_EXTRAPOLATE_HIST = 2 };
+
+/* status codes */
+enum {
+    IB200_OK = 0,
+    IB200_ERR_NULL = -1,          /* null pointer argument */
+    IB200_ERR_DTYPE = -2,         /* unknown dtype code */
+    IB200_ERR_DIM = -3,           /* dim not in {1,2,3} (reference: nd.py handles any dim on CPU) */
+    IB200_ERR_BOUND = -4,         /* bound code not in 0..6 (autograd.py:95 ValueError) */
+    IB200_ERR_ORDER = -5,         /* order not in 0..7 (autograd.py:145 ValueError) */
+    IB200_ERR_SHAPE = -6,         /* non-positive extent / inconsistent shapes */
+    IB200_ERR_BOUND_UNSUPPORTED = -7, /* prefilter with dst1/dst2 (coeff.py:237-254 NotImplementedError) */
+    IB200_ERR_SCRATCH = -8,       /* scratch buffer required but missing */
+    IB200_ERR_EXTRAPOLATE = -9,   /* extrapolate not in {0,1,2} */
+    IB200_ERR_TOO_LARGE = -10,    /* a single volume exceeds 2^31-1 voxels */
+    IB200_ERR_CUDA = -1000        /* IB200_ERR_CUDA - (int)cudaError_t */
+};
+
+/* behaviour switches (ib200_problem.flags) */
+enum {
+    IB200_FLAG_NONE = 0,
+    /* never take the shared-memory tiled fast paths (A/B testing, profiling) */
+    IB200_FLAG_NO_TILES = 1u << 0,
+    /* reproduce the reference's sign error for d/dx of the order-1 spline on an
+     * axis of a mixed-order call (splines.py:96-97); default is the true derivative */
+    IB200_FLAG_REF_LINEAR_GRAD_SIGN = 1u << 1
+};
+
+/*
+ * Geometry + options shared by the six push/pull entry points.  It carries
+ * what pushpull.py's functions receive as (bound: List[int],
+ * interpolation: List[int], extrapolate: int) plus the tensor shapes/strides
+ * that the reference reads off the torch tensors.
+ */
+typedef struct ib200_problem {
+    int32_t dim;            /* number of spatial dimensions D: 1, 2 or 3 */
+    int32_t dtype;          /* IB200_F16 / F32 / F64 / BF16, same for every tensor */
+    int32_t extrapolate;    /* 0 / 1 / 2, nd.py:11-27 */
+    int32_t device;         /* CUDA device ordinal that owns every pointer */
+    int32_t bound[3];       /* per spatial axis, already padded (jit_utils.py:10-15) */
+    int32_t order[3];       /* spline order 0..7 per spatial axis, already padded */
+    uint32_t flags;         /* IB200_FLAG_* */
+    uint32_t reserved;
+    int64_t batch;          /* B = max over operands (operands with B=1 use stride 0) */
+    int64_t channels;       /* C */
+    int64_t vol_shape[3];   /* spatial shape of the volume that is gathered from
+                               (pull/grad/hess) or scattered into (push/count/pushgrad) */
+    int64_t pts_shape[3];   /* spatial shape of the grid lattice */
+    int64_t vol_stride[5];  /* element strides B, C, X, Y, Z of an INPUT volume (pull/grad/hess) */
+    int64_t grid_stride[5]; /* element strides B, X, Y, Z, D of the grid */
+    int64_t img_stride[6];  /* element strides B, C, X, Y, Z, D of an INPUT image living on the
+                               grid lattice (push / pushgrad); the D entry is used by pushgrad only */
+} ib200_problem;
+
+/* out (B, C, *pts_shape) = pull(vol, grid).  Replaces pushpull.grid_pull
+ * (interpol/pushpull.py:35-66 -> nd.py:81-143 / iso1.py / iso0.py). */
+IB200_API int ib200_pull(const ib200_problem *p, const void *vol, const void *grid,
+               void *out, void *stream);
+
+/* out (B, C, *pts_shape, D) = spatial gradient of the interpolated volume.
+ * Replaces pushpull.grid_grad (interpol/pushpull.py:146-172 -> nd.py:217-288). */
+IB200_API int ib200_grad(const ib200_problem *p, const void *vol, const void *grid,
+               void *out, void *stream);
+
+/* out (B, C, *pts_shape, D, D) = Hessian.  Replaces pushpull.grid_hess
+ * (interpol/pushpull.py:207-233 -> nd.py:368-464); only used by GridGrad.backward. */
+IB200_API int ib200_hess(const ib200_problem *p, const void *vol, const void *grid,
+               void *out, void *stream);
+
+/* vol_out (B, C, *vol_shape) = splat of img (B, C, *pts_shape) along grid; the
+ * callee zero-fills vol_out.  Replaces pushpull.grid_push
+ * (interpol/pushpull.py:70-102 -> nd.py:147-213).
+ * `scratch`: required for F16/BF16 (float32 accumulation volume of
+ * ib200_scratch_bytes() bytes), ignored (may be NULL) otherwise. */
+IB200_API int ib200_push(const ib200_problem *p, const void *img, const void *grid,
+               void *vol_out, void *scratch, void *stream);
+
+/* vol_out (B, 1, *vol_shape) = splat of ones.  Replaces pushpull.grid_count
+ * (interpol/pushpull.py:106-142); `channels` is ignored (treated as 1). */
+IB200_API int ib200_count(const ib200_problem *p, const void *grid, void *vol_out,
+                void *scratch, void *stream);
+
+/* vol_out (B, C, *vol_shape) = adjoint of ib200_grad applied to
+ * img (B, C, *pts_shape, D).  Replaces pushpull.grid_pushgrad
+ * (interpol/pushpull.py:175-204 -> nd.py:292-364); only used by GridGrad.backward. */
+IB200_API int ib200_pushgrad(const ib200_problem *p, const void *img, const void *grid,
+                   void *vol_out, void *scratch, void *stream);
+
+/* Fused backward of pull w.r.t. the grid: out (B, *pts_shape, D) =
+ * sum_c grad(vol, grid)[b,c,...,:] * gout[b,c,...] without materialising the
+ * (B, C, *pts, D) temporary of pushpull.grid_pull_backward
+ * (interpol/pushpull.py:254-257).  `gout` uses img_stride (B, C, X, Y, Z). */
+IB200_API int ib200_pull_backward_grid(const ib200_problem *p, const void *vol, const void *grid,
+                             const void *gout, void *out, void *stream);
+
+/* Number of bytes of scratch the scatter entry points need for this problem
+ * (0 for F32/F64). */
+IB200_API size_t ib200_scratch_bytes(const ib200_problem *p);
+
+/* In-place spline prefilter along one axis of a dense tensor viewed as
+ * (outer, n, inner).  Replaces coeff.spline_coeff (interpol/coeff.py:288-313
+ * -> coeff.filter :258-284); orders 0/1 are no-ops, n == 1 is a no-op,
+ * bounds zero->dct1 and replicate->dct2 alias like coeff.py:237-252. */
+IB200_API int ib200_spline_coeff(void *data, int32_t dtype, int64_t outer, int64_t n,
+                       int64_t inner, int32_t bound, int32_t order,
+                       int32_t device, void *stream);
+
+/* Introspection */
+IB200_API int ib200_abi_version(void);
+IB200_API const char *ib200_error_string(int status);
+/* name of the kernel variant the last call on this thread dispatched to */
+IB200_API const char *ib200_last_kernel(void);
+/* number of kernel launches issued by this library since load (all threads) */
+IB200_API uint64_t ib200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INTERPOL_B200_H */

@@ -1,0 +1,293 @@
+// Spline prefilter: separable causal / anti-causal recursive (IIR) filter, one
+// axis per launch, lines batched over threads.
+//
+// The tensor is viewed as (outer, n, inner) and filtered along n, in place.
+//  * inner > 1 : a warp owns 32 adjacent lines (consecutive `inner` index); the
+//    [n x 32] tile is staged in shared memory with cp.async (16 B per lane when
+//    alignment allows), each lane then runs all poles of its line out of its
+//    own bank-conflict-free column, and the tile is written back coalesced:
+//    one HBM read + one HBM write per axis whatever the number of poles.
+//  * inner == 1: the lines themselves are contiguous; a CTA stages L whole
+//    lines (a contiguous block of L*n elements) with a padded, odd row stride.
+//  * lines too long for shared memory fall back to in-place global recursion.
+//
+// Replaces interpol/coeff.py:258-284 (filter) with the boundary conditions of
+// coeff.py:82-227 (dct1/dct2/dft initial+final; zero->dct1, replicate->dct2).
+#include <cstdio>
+#include <cmath>
+#include "common.cuh"
+
+namespace ib200 {
+
+struct CoeffParams {
+    i64 outer, n, inner;
+    int kind;            // 1: dct1, 2: dct2, 6: dft
+    int npoles;
+    double gain;
+    double pole[3];      // exact poles (recursions, finals)                coeff.py:276,281
+    double pp[3];        // pole rounded through float32 (power vectors)    SURVEY Q11
+    double c1[3];        // dct1: pole^(n-1); dct2: pole^n; dft: pole^K
+    int K[3];            // truncation length ceil(-30/log|pole|) (dft: min(K, n))
+    int K2[3];           // length after which pp^k is < 1e-40 (dct2 exact sum cut-off)
+};
+
+// ------------------------------------------------------------------------
+// All poles of one line held in shared (or global) memory with element stride st.
+template <typename R, typename P>
+__device__ __forceinline__ void filter_line(P s, const int st, const int n, const CoeffParams &cp) {
+#define S(i) s[(i64)(i) * st]
+    for (int p = 0; p < cp.npoles; ++p) {
+        const R pole = (R)cp.pole[p];
+        const R pp = (R)cp.pp[p];
+        R init;
+        if (cp.kind == 1) {                      // dct1_initial, coeff.py:109-149
+            if (cp.K[p] < n) {
+                R acc = R(0), a = R(1);
+                for (int k = 0; k < cp.K[p]; ++k) { acc = fma((R)S(k), a, acc); a *= pp; }
+                init = acc;
+            } else {
+                const R pn = (R)cp.c1[p];
+                const R pn2 = (R)(cp.c1[p] * cp.c1[p]);
+                R out = (R)S(0) + pn * (R)S(n - 1);
+                if (n > 2) {
+                    R acc = R(0), a = pp;
+                    for (int k = 1; k < n - 1; ++k) { acc = fma((R)S(k), a + pn2 / a, acc); a *= pp; }
+                    out += acc;
+                }
+                init = out / (R)(1. - cp.c1[p] * cp.c1[p]);
+            }
+        } else if (cp.kind == 2) {               // dct2_initial, coeff.py:153-179
+            const R pn = (R)cp.c1[p];
+            R acc = R(0), a = R(1);
+            const int kmax = n < cp.K2[p] ? n : cp.K2[p];
+            for (int k = 0; k < kmax; ++k) { acc = fma((R)S(k), a, acc); a *= pp; }
+            if (pn != R(0)) {
+                R acc2 = R(0), b = R(1);
+                for (int k = n - 1; k >= n - kmax; --k) { acc2 = fma((R)S(k), b, acc2); b *= pp; }
+                acc = fma(pn, acc2, acc);
+            }
+            init = fma(acc, (R)(cp.pole[p] / (1. - cp.c1[p] * cp.c1[p])), (R)S(0));
+        } else {                                 // dft_initial, coeff.py:82-105
+            R acc = R(0), a = pp;
+            for (int j = 1; j < cp.K[p]; ++j) { acc = fma((R)S(n - j), a, acc); a *= pp; }
+            init = (acc + (R)S(0)) / (R)(1. - cp.c1[p]);
+        }
+        // causal recursion, coeff.py:275-276
+        R prev = init;
+        S(0) = prev;
+#pragma unroll 8
+        for (int i = 1; i < n; ++i) { prev = fma(pole, prev, (R)S(i)); S(i) = prev; }
+        // final condition (reads the causally filtered line)
+        R fin;
+        if (cp.kind == 1) {                      // dct1_final, coeff.py:210-216
+            fin = (pole * (R)S(n - 2) + (R)S(n - 1)) * (R)(cp.pole[p] / (cp.pole[p] * cp.pole[p] - 1.));
+        } else if (cp.kind == 2) {               // dct2_final, coeff.py:220-227
+            fin = (R)S(n - 1) * (R)(cp.pole[p] / (cp.pole[p] - 1.));
+        } else {                                 // dft_final, coeff.py:183-206
+            R acc = R(0), a = pp * pp;
+            for (int k = 0; k < cp.K[p] - 1; ++k) { acc = fma((R)S(k), a, acc); a *= pp; }
+            fin = fma(pole, (R)S(n - 1), acc) / (R)(cp.c1[p] - 1.);
+        }
+        // anti-causal recursion, coeff.py:280-281
+        prev = fin;
+        S(n - 1) = prev;
+#pragma unroll 8
+        for (int i = n - 2; i >= 0; --i) { prev = pole * (prev - (R)S(i)); S(i) = prev; }
+    }
+#undef S
+}
+
+// proxy so that filter_line can run directly on 16-bit global storage
+template <typename T>
+struct GlobalRef {
+    T *p;
+    __device__ __forceinline__ operator float() const { return Traits<T>::load_rw(p); }
+    __device__ __forceinline__ void operator=(float v) { Traits<T>::store(p, v); }
+};
+template <typename T>
+struct GlobalLine {
+    T *base;
+    __device__ __forceinline__ GlobalRef<T> operator[](i64 i) const { return GlobalRef<T>{base + i}; }
+};
+
+// ---------------------------------------------------------------- kernels --
+
+// inner > 1.  blockDim.x = 32 * W; every warp owns a tile of 32 lines.
+template <typename T>
+__global__ void __launch_bounds__(128)
+coeff_strided_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data) {
+    typedef typename Traits<T>::Real R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = (int)cp.n;
+    R *tile = reinterpret_cast<R *>(smem_raw) + (size_t)warp * n * 32;
+    const i64 tiles_per_outer = (cp.inner + 31) / 32;
+    const i64 ntiles = cp.outer * tiles_per_outer;
+    const R gain = (R)cp.gain;
+    for (i64 tidx = (i64)blockIdx.x * nwarp + warp; tidx < ntiles; tidx += (i64)gridDim.x * nwarp) {
+        const i64 o = tidx / tiles_per_outer;
+        const i64 k0 = (tidx - o * tiles_per_outer) * 32;
+        const bool active = k0 + lane < cp.inner;
+        T *g = data + o * cp.n * cp.inner + k0 + lane;
+        if (active) {
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) tile[i * 32 + lane] = Traits<T>::load_rw(g + (i64)i * cp.inner) * gain;
+            filter_line<R>(tile + lane, 32, n, cp);
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) Traits<T>::store(g + (i64)i * cp.inner, tile[i * 32 + lane]);
+        }
+        __syncwarp();
+    }
+}
+
+// inner == 1.  A CTA stages L = blockDim.x whole lines (contiguous in memory).
+template <typename T>
+__global__ void __launch_bounds__(256)
+coeff_contig_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data, int row_stride) {
+    typedef typename Traits<T>::Real R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tile = reinterpret_cast<R *>(smem_raw);
+    const int n = (int)cp.n, L = blockDim.x;
+    const i64 nblk = (cp.outer + L - 1) / L;
+    const R gain = (R)cp.gain;
+    for (i64 blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const i64 l0 = blk * L;
+        const int nl = (int)((cp.outer - l0) < L ? (cp.outer - l0) : L);
+        T *g = data + l0 * n;
+        const int count = nl * n;
+        for (int e = threadIdx.x; e < count; e += L) {
+            const int l = e / n, i = e - l * n;
+            tile[l * row_stride + i] = Traits<T>::load_rw(g + e) * gain;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nl) filter_line<R>(tile + threadIdx.x * row_stride, 1, n, cp);
+        __syncthreads();
+        for (int e = threadIdx.x; e < count; e += L) {
+            const int l = e / n, i = e - l * n;
+            Traits<T>::store(g + e, tile[l * row_stride + i]);
+        }
+        __syncthreads();
+    }
+}
+
+// fallback for lines that do not fit in shared memory: in-place on global.
+template <typename T>
+__global__ void __launch_bounds__(128)
+coeff_global_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data) {
+    typedef typename Traits<T>::Real R;
+    const i64 nlines = cp.outer * cp.inner;
+    const R gain = (R)cp.gain;
+    for (i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (i64)gridDim.x * blockDim.x) {
+        const i64 o = l / cp.inner, k = l - o * cp.inner;
+        T *g = data + o * cp.n * cp.inner + k;
+        for (i64 i = 0; i < cp.n; ++i) Traits<T>::store(g + i * cp.inner, Traits<T>::load_rw(g + i * cp.inner) * gain);
+        if (sizeof(T) == sizeof(R)) filter_line<R>(reinterpret_cast<R *>(g), (int)cp.inner, (int)cp.n, cp);
+        else filter_line<R>(GlobalLine<T>{g}, (int)cp.inner, (int)cp.n, cp);
+    }
+}
+// ---------------------------------------------------------------- launch --
+
+static int get_poles(int order, double *poles) {   // coeff.py:35-65
+    switch (order) {
+    case 2: poles[0] = sqrt(8.) - 3.; return 1;
+    case 3: poles[0] = sqrt(3.) - 2.; return 1;
+    case 4:
+        poles[0] = sqrt(664. - sqrt(438976.)) + sqrt(304.) - 19.;
+        poles[1] = sqrt(664. + sqrt(438976.)) - sqrt(304.) - 19.;
+        return 2;
+    case 5:
+        poles[0] = sqrt(67.5 - sqrt(4436.25)) + sqrt(26.25) - 6.5;
+        poles[1] = sqrt(67.5 + sqrt(4436.25)) - sqrt(26.25) - 6.5;
+        return 2;
+    case 6:
+        poles[0] = -0.488294589303044755130118038883789062112279161239377608394;
+        poles[1] = -0.081679271076237512597937765737059080653379610398148178525368;
+        poles[2] = -0.00141415180832581775108724397655859252786416905534669851652709;
+        return 3;
+    case 7:
+        poles[0] = -0.5352804307964381655424037816816460718339231523426924148812;
+        poles[1] = -0.122554615192326690515272264359357343605486549427295558490763;
+        poles[2] = -0.0091486948096082769285930216516478534156925639545994482648003;
+        return 3;
+    }
+    return 0;
+}
+
+template <typename T>
+static int launch_typed(const CoeffParams &cp, void *data, cudaStream_t stream) {
+    typedef typename Traits<T>::Real R;
+    const size_t kSmemCap = 200 * 1024;
+    T *d = (T *)data;
+    if (cp.inner > 1) {
+        const size_t per_warp = (size_t)cp.n * 32 * sizeof(R);
+        if (per_warp <= kSmemCap) {
+            int warps = 1;   // one warp per CTA keeps the smem granularity fine
+            const i64 ntiles = cp.outer * ((cp.inner + 31) / 32);
+            i64 blocks = (ntiles + warps - 1) / warps;
+            const i64 cap = (i64)kNumSMs * 32;
+            if (blocks > cap) blocks = cap;
+            const size_t smem = per_warp * warps;
+            IB200_CUDA_CHECK(cudaFuncSetAttribute(coeff_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            coeff_strided_kernel<T><<<(unsigned)blocks, 32 * warps, smem, stream>>>(cp, d);
+            note_launch("coeff_strided");
+            IB200_CUDA_CHECK(cudaGetLastError());
+            return IB200_OK;
+        }
+    } else {
+        int row_stride = (int)cp.n | 1;   // odd stride: lane l, element i -> distinct banks
+        int L = 256;
+        while (L > 32 && (size_t)L * row_stride * sizeof(R) > 64 * 1024) L >>= 1;
+        const size_t smem = (size_t)L * row_stride * sizeof(R);
+        if (smem <= kSmemCap) {
+            i64 blocks = (cp.outer + L - 1) / L;
+            const i64 cap = (i64)kNumSMs * 16;
+            if (blocks > cap) blocks = cap;
+            IB200_CUDA_CHECK(cudaFuncSetAttribute(coeff_contig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            coeff_contig_kernel<T><<<(unsigned)blocks, L, smem, stream>>>(cp, d, row_stride);
+            note_launch("coeff_contig");
+            IB200_CUDA_CHECK(cudaGetLastError());
+            return IB200_OK;
+        }
+    }
+    const i64 nlines = cp.outer * cp.inner;
+    i64 blocks = (nlines + 127) / 128;
+    if (blocks > (i64)kNumSMs * 16) blocks = (i64)kNumSMs * 16;
+    coeff_global_kernel<T><<<(unsigned)blocks, 128, 0, stream>>>(cp, d);
+    note_launch("coeff_global");
+    IB200_CUDA_CHECK(cudaGetLastError());
+    return IB200_OK;
+}
+
+int launch_coeff(void *data, int dtype, i64 outer, i64 n, i64 inner, int bound, int order,
+                 cudaStream_t stream) {
+    if (order <= 1 || n == 1 || outer * inner == 0) return IB200_OK;   // coeff.py:263-264, 306-307
+    CoeffParams cp;
+    cp.outer = outer; cp.n = n; cp.inner = inner;
+    if (bound == IB200_BOUND_ZERO || bound == IB200_BOUND_DCT1) cp.kind = 1;          // coeff.py:237-252
+    else if (bound == IB200_BOUND_REPLICATE || bound == IB200_BOUND_DCT2) cp.kind = 2;
+    else if (bound == IB200_BOUND_DFT) cp.kind = 6;
+    else return IB200_ERR_BOUND_UNSUPPORTED;
+    cp.npoles = get_poles(order, cp.pole);
+    cp.gain = 1.;
+    for (int p = 0; p < 3; ++p) { cp.pp[p] = 0; cp.c1[p] = 0; cp.K[p] = 0; cp.K2[p] = 0; if (p >= cp.npoles) cp.pole[p] = 0; }
+    for (int p = 0; p < cp.npoles; ++p) {
+        const double pole = cp.pole[p];
+        cp.gain *= (1. - pole) * (1. - 1. / pole);                                    // coeff.py:69-73
+        cp.pp[p] = (double)(float)pole;
+        i64 K = (i64)ceil(-30. / log(fabs(pole)));
+        cp.K2[p] = (int)ceil(log(1e-40) / log(fabs(pole)));
+        if (cp.kind == 1) { cp.c1[p] = pow(pole, (double)(n - 1)); }
+        else if (cp.kind == 2) { cp.c1[p] = pow(pole, (double)n); }
+        else { if (K > n) K = n; cp.c1[p] = pow(pole, (double)K); }
+        cp.K[p] = (int)(K > 0x7fffffff ? 0x7fffffff : K);
+    }
+    switch (dtype) {
+    case IB200_F32: return launch_typed<float>(cp, data, stream);
+    case IB200_F64: return launch_typed<double>(cp, data, stream);
+    case IB200_F16: return launch_typed<__half>(cp, data, stream);
+    case IB200_BF16: return launch_typed<__nv_bfloat16>(cp, data, stream);
+    }
+    return IB200_ERR_DTYPE;
+}
+
+}  // namespace ib200

@@ -1,0 +1,267 @@
+"""High-level API: same functions, keyword arguments and defaults as the
+reference's `interpol/api.py` (grid_pull :149, grid_push :215, grid_count :265,
+grid_grad :302, spline_coeff :347, spline_coeff_nd :398, grid helpers :467-572).
+
+Shapes follow the reference: volumes `(..., [channel], *spatial)`, grids
+`(..., *spatial, dim)` in voxel units.  Tensors on a CUDA device are processed
+in place on that device; CPU tensors are staged to the current CUDA device
+(asynchronously when pinned), processed by the same kernels and returned on
+the CPU -- there is no CPU implementation.
+"""
+import torch
+
+from .utils import expanded_shape, matvec, meshgrid_ij
+from .autograd import (GridPull, GridPush, GridCount, GridGrad,
+                       SplineCoeff, SplineCoeffND)
+
+__all__ = [
+    'pull', 'push', 'count',
+    'grid_pull', 'grid_push', 'grid_count', 'grid_grad',
+    'spline_coeff', 'spline_coeff_nd',
+    'identity_grid', 'add_identity_grid', 'add_identity_grid_', 'affine_grid',
+]
+
+
+# --------------------------------------------------------------------------
+# host <-> device staging
+# --------------------------------------------------------------------------
+
+def _stage(*tensors):
+    """Move CPU tensors to the current CUDA device.  Returns (tensors, back)
+    where `back(out)` returns the result to where the inputs lived."""
+    if all(t is None or t.is_cuda for t in tensors):
+        return tensors, (lambda out: out)
+    if not torch.cuda.is_available():
+        raise RuntimeError('interpol_b200 needs a CUDA device (no CPU fallback)')
+    dev = None
+    for t in tensors:
+        if t is not None and t.is_cuda:
+            dev = t.device
+    if dev is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    staged = tuple(None if t is None else (t if t.is_cuda else t.to(dev, non_blocking=True))
+                   for t in tensors)
+    return staged, (lambda out: out.cpu())
+
+
+# --------------------------------------------------------------------------
+# shape canonicalisation (reference: api.py:93-146)
+# --------------------------------------------------------------------------
+
+def _preproc(grid, input=None, mode=None):
+    """Broadcast batch dimensions and reshape to (B, C, *spatial) / (B, *spatial, D).
+    Batch broadcasting uses `expand` (zero strides): the kernels honour strides so
+    no copy is made unless `reshape` has to merge non-mergeable axes."""
+    dim = grid.shape[-1]
+    if input is None:
+        spatial = grid.shape[-dim-1:-1]
+        batch = grid.shape[:-dim-1]
+        grid = grid.reshape([-1, *spatial, dim])
+        info = dict(batch=batch, channel=[1] if batch else [], dim=dim)
+        return grid, info
+
+    grid_spatial = grid.shape[-dim-1:-1]
+    grid_batch = grid.shape[:-dim-1]
+    input_spatial = input.shape[-dim:]
+    channel = 0 if input.dim() == dim else input.shape[-dim-1]
+    input_batch = input.shape[:-dim-1]
+
+    if mode == 'push':
+        grid_spatial = input_spatial = expanded_shape(grid_spatial, input_spatial)
+
+    batch = expanded_shape(grid_batch, input_batch)
+    grid = grid.expand([*batch, *grid_spatial, dim])
+    grid = grid.reshape([-1, *grid_spatial, dim])
+    input = input.expand([*batch, channel or 1, *input_spatial])
+    input = input.reshape([-1, channel or 1, *input_spatial])
+
+    out_channel = [channel] if channel else ([1] if batch else [])
+    info = dict(batch=batch, channel=out_channel, dim=dim)
+    return grid, input, info
+
+
+def _postproc(out, shape_info, mode):
+    """reference: api.py:133-146"""
+    dim = shape_info['dim']
+    if mode != 'grad':
+        spatial = out.shape[-dim:]
+        feat = []
+    else:
+        spatial = out.shape[-dim-1:-1]
+        feat = [out.shape[-1]]
+    batch = shape_info['batch']
+    channel = shape_info['channel']
+    return out.reshape([*batch, *channel, *spatial, *feat])
+
+
+# --------------------------------------------------------------------------
+# public functions
+# --------------------------------------------------------------------------
+
+def grid_pull(input, grid, interpolation='linear', bound='zero',
+              extrapolate=False, prefilter=False):
+    """Sample an image with respect to a deformation field.
+
+    input : (..., [channel], *inshape) tensor;  grid : (..., *outshape, dim) tensor
+    interpolation : int | str | list, default 'linear' (orders 0..7)
+    bound : str | int | list, default 'zero' (zero, replicate, dct1, dct2, dst1, dst2, dft)
+    extrapolate : bool | int, default False;  prefilter : bool, default False
+    returns (..., [channel], *outshape)
+
+    Integer inputs are treated as label maps: every label is resampled as a
+    soft mask and the arg-max label is returned (reference: api.py:194-205).
+    """
+    (input, grid), back = _stage(input, grid)
+    grid, input, shape_info = _preproc(grid, input)
+    batch, channel = input.shape[:2]
+    dim = grid.shape[-1]
+
+    if not input.dtype.is_floating_point:
+        out = input.new_zeros([batch, channel, *grid.shape[1:-1]])
+        pmax = grid.new_zeros([batch, channel, *grid.shape[1:-1]])
+        for label in input.unique():
+            soft = (input == label).to(grid.dtype)
+            if prefilter:
+                soft = spline_coeff_nd(soft, interpolation=interpolation,
+                                       bound=bound, dim=dim, inplace=True)
+            soft = GridPull.apply(soft, grid, interpolation, bound, extrapolate)
+            out[soft > pmax] = label
+            pmax = torch.max(pmax, soft)
+    else:
+        if prefilter:
+            input = spline_coeff_nd(input, interpolation=interpolation,
+                                    bound=bound, dim=dim)
+        out = GridPull.apply(input, grid, interpolation, bound, extrapolate)
+
+    return back(_postproc(out, shape_info, mode='pull'))
+
+
+def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
+              extrapolate=False, prefilter=False):
+    """Splat an image with respect to a deformation field (adjoint of pull).
+
+    input : (..., [channel], *inshape);  grid : (..., *inshape, dim)
+    shape : output spatial shape, default inshape
+    returns (..., [channel], *shape)        (reference: api.py:215-262)
+    """
+    (input, grid), back = _stage(input, grid)
+    grid, input, shape_info = _preproc(grid, input, mode='push')
+    dim = grid.shape[-1]
+
+    if shape is None:
+        shape = tuple(input.shape[2:])
+
+    out = GridPush.apply(input, grid, shape, interpolation, bound, extrapolate)
+    if prefilter:
+        out = spline_coeff_nd(out, interpolation=interpolation, bound=bound,
+                              dim=dim, inplace=True)
+    return back(_postproc(out, shape_info, mode='push'))
+
+
+def grid_count(grid, shape=None, interpolation='linear', bound='zero',
+               extrapolate=False):
+    """Splatting weights of a deformation field (push of an image of ones).
+
+    grid : (..., *inshape, dim);  returns (..., [1], *shape)   (reference: api.py:265-299)
+    """
+    (grid,), back = _stage(grid)
+    grid, shape_info = _preproc(grid)
+    out = GridCount.apply(grid, shape, interpolation, bound, extrapolate)
+    return back(_postproc(out, shape_info, mode='count'))
+
+
+def grid_grad(input, grid, interpolation='linear', bound='zero',
+              extrapolate=False, prefilter=False):
+    """Sample the spatial gradients of an image with respect to a deformation field.
+
+    returns (..., [channel], *outshape, dim)                  (reference: api.py:302-344)
+    """
+    (input, grid), back = _stage(input, grid)
+    grid, input, shape_info = _preproc(grid, input)
+    dim = grid.shape[-1]
+    if prefilter:
+        input = spline_coeff_nd(input, interpolation, bound, dim)
+    out = GridGrad.apply(input, grid, interpolation, bound, extrapolate)
+    return back(_postproc(out, shape_info, mode='grad'))
+
+
+def spline_coeff(input, interpolation='linear', bound='dct2', dim=-1,
+                 inplace=False):
+    """Interpolating spline coefficients along one dimension
+    (reference: api.py:347-395; only dct1/dct2/dft and their aliases zero/replicate)."""
+    if not input.is_cuda:
+        (x,), back = _stage(input)
+        out = back(SplineCoeff.apply(x, bound, interpolation, dim, False))
+        if inplace:
+            input.copy_(out)
+            return input
+        return out
+    return SplineCoeff.apply(input, bound, interpolation, dim, inplace)
+
+
+def spline_coeff_nd(input, interpolation='linear', bound='dct2', dim=None,
+                    inplace=False):
+    """Interpolating spline coefficients along the last `dim` dimensions
+    (reference: api.py:398-445)."""
+    if not input.is_cuda:
+        (x,), back = _stage(input)
+        out = back(SplineCoeffND.apply(x, bound, interpolation, dim, False))
+        if inplace:
+            input.copy_(out)
+            return input
+        return out
+    return SplineCoeffND.apply(input, bound, interpolation, dim, inplace)
+
+
+# aliases
+pull = grid_pull
+push = grid_push
+count = grid_count
+
+
+# --------------------------------------------------------------------------
+# grid helpers (reference: api.py:467-572) -- plain torch ops, any device
+# --------------------------------------------------------------------------
+
+def identity_grid(shape, dtype=None, device=None):
+    """Identity deformation field in voxel units: (*shape, dim)."""
+    mesh1d = [torch.arange(float(s), dtype=dtype, device=device) for s in shape]
+    return torch.stack(meshgrid_ij(*mesh1d), dim=-1)
+
+
+def add_identity_grid_(disp):
+    """Add the identity grid to a displacement field (..., *spatial, dim), in place."""
+    dim = disp.shape[-1]
+    spatial = disp.shape[-dim-1:-1]
+    mesh1d = [torch.arange(s, dtype=disp.dtype, device=disp.device) for s in spatial]
+    for i, g in enumerate(meshgrid_ij(*mesh1d)):
+        disp[..., i].add_(g)
+    return disp
+
+
+def add_identity_grid(disp):
+    """Add the identity grid to a displacement field (out of place)."""
+    return add_identity_grid_(disp.clone())
+
+
+def affine_grid(mat, shape):
+    """Dense transformation grid (..., *shape, D) from affine matrices (..., D[+1], D+1)."""
+    mat = torch.as_tensor(mat)
+    shape = list(shape)
+    nb_dim = mat.shape[-1] - 1
+    if nb_dim != len(shape):
+        raise ValueError('Dimension of the affine matrix ({}) and shape ({}) '
+                         'are not the same.'.format(nb_dim, len(shape)))
+    if mat.shape[-2] not in (nb_dim, nb_dim+1):
+        raise ValueError('First argument should be matrices of shape '
+                         '(..., {0}, {1}) or (..., {1}, {1}) but got {2}.'
+                         .format(nb_dim, nb_dim+1, mat.shape))
+    grid = identity_grid(shape, mat.dtype, mat.device)
+    lin = mat[..., :nb_dim, :nb_dim]
+    off = mat[..., :nb_dim, -1]
+    # (the reference's batched branch, api.py:560-565, indexes the wrong axes and
+    #  raises; the intended broadcast is implemented here)
+    for _ in range(nb_dim):
+        lin = lin.unsqueeze(-3)
+        off = off.unsqueeze(-2)
+    return matvec(lin, grid) + off

@@ -1,0 +1,275 @@
+"""Non-differentiable forward/backward building blocks -- same names, argument
+order and shapes as the reference's `interpol/pushpull.py`, but every function
+is a single call into the C ABI (include/interpol_b200.h) instead of a loop of
+ATen ops.
+
+    inp  : (B, C, *spatial_in)      grid : (B, *spatial_out, D)
+    bound: List[int]  interpolation: List[int]  extrapolate: int
+
+Reference: interpol/pushpull.py:35-233 (forward), :237-325 (backward algebra).
+"""
+import ctypes
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import Problem
+
+Tensor = torch.Tensor
+
+# module-level switches (A/B testing, parity experiments)
+flags = 0
+
+
+def pad_list_int(x: List[int], dim: int) -> List[int]:
+    """jit_utils.py:10-15"""
+    x = list(x)
+    if len(x) < dim:
+        x = x + x[-1:] * (dim - len(x))
+    if len(x) > dim:
+        x = x[:dim]
+    return x
+
+
+def _common_dtype(*tensors):
+    dt = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.dtype.is_floating_point:
+            raise TypeError('interpol_b200 kernels need floating point tensors (got %s)' % t.dtype)
+        dt = t.dtype if dt is None else torch.promote_types(dt, t.dtype)
+    if dt not in _lib.DTYPE_CODE:
+        raise TypeError('unsupported dtype %s' % dt)
+    return dt
+
+
+def _problem(dim, dtype, device, bound, interpolation, extrapolate, batch, channels,
+             vol_shape, pts_shape):
+    if dim < 1 or dim > 3:
+        # nd.py handles any dimension through ATen; there is no CPU fallback here
+        raise NotImplementedError('interpol_b200 supports 1, 2 or 3 spatial dimensions (got %d)' % dim)
+    p = Problem()
+    p.dim = dim
+    p.dtype = _lib.DTYPE_CODE[dtype]
+    p.extrapolate = int(extrapolate)
+    p.device = device.index if device.index is not None else torch.cuda.current_device()
+    b = pad_list_int(bound, dim)
+    o = pad_list_int(interpolation, dim)
+    for d in range(dim):
+        p.bound[d] = int(b[d])
+        p.order[d] = int(o[d])
+        p.vol_shape[d] = int(vol_shape[d])
+        p.pts_shape[d] = int(pts_shape[d])
+    p.flags = flags
+    p.batch = batch
+    p.channels = channels
+    return p
+
+
+def _bstride(t, batch):
+    """batch stride with broadcasting of a singleton batch (reference: expand)"""
+    return 0 if (t.shape[0] == 1 and batch != 1) else t.stride(0)
+
+
+def _set_vol(p, vol, batch, dim):
+    p.vol_stride[0] = _bstride(vol, batch)
+    p.vol_stride[1] = vol.stride(1)
+    for d in range(dim):
+        p.vol_stride[2 + d] = vol.stride(2 + d)
+
+
+def _set_grid(p, grid, batch, dim):
+    p.grid_stride[0] = _bstride(grid, batch)
+    for d in range(dim):
+        p.grid_stride[1 + d] = grid.stride(1 + d)
+    p.grid_stride[1 + dim] = grid.stride(1 + dim)
+
+
+def _set_img(p, img, batch, dim, comp=False):
+    p.img_stride[0] = _bstride(img, batch)
+    p.img_stride[1] = img.stride(1)
+    for d in range(dim):
+        p.img_stride[2 + d] = img.stride(2 + d)
+    if comp:
+        p.img_stride[2 + dim] = img.stride(2 + dim)
+
+
+def _batch(*tensors):
+    b = 1
+    for t in tensors:
+        if t.shape[0] != 1:
+            if b != 1 and t.shape[0] != b:
+                raise ValueError('Incompatible batch sizes: %d and %d' % (b, t.shape[0]))
+            b = t.shape[0]
+    if any(t.shape[0] == 0 for t in tensors):
+        b = 0
+    return b
+
+
+def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gout=None):
+    _lib.require_cuda(inp, grid, gout)
+    dim = grid.shape[-1]
+    if grid.dim() != dim + 2 or inp.dim() != dim + 2:
+        raise ValueError('expected inp (B, C, *spatial) and grid (B, *spatial, D)')
+    dtype = _common_dtype(inp, grid, gout)
+    inp = inp.to(dtype)
+    grid = grid.to(dtype)
+    batch = _batch(inp, grid) if gout is None else _batch(inp, grid, gout)
+    channels = inp.shape[1]
+    ishape = inp.shape[2:]
+    oshape = grid.shape[1:-1]
+    p = _problem(dim, dtype, grid.device, bound, interpolation, extrapolate, batch, channels,
+                 ishape, oshape)
+    _set_vol(p, inp, batch, dim)
+    _set_grid(p, grid, batch, dim)
+    L = _lib.lib()
+    with torch.cuda.device(grid.device):
+        s = _lib.stream_ptr(grid.device)
+        if gout is None:
+            out = torch.empty([batch, channels, *oshape, *trailing(dim)], dtype=dtype, device=grid.device)
+            st = getattr(L, fn_name)(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid), _lib.ptr(out), s)
+        else:
+            gout = gout.to(dtype)
+            _set_img(p, gout, batch, dim)
+            out = torch.empty([batch, *oshape, dim], dtype=dtype, device=grid.device)
+            st = L.ib200_pull_backward_grid(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid),
+                                            _lib.ptr(gout), _lib.ptr(out), s)
+    _lib.check(st)
+    return out
+
+
+def grid_pull(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int):
+    """(B, C, *spatial_in), (B, *spatial_out, D) -> (B, C, *spatial_out)
+    Reference: interpol/pushpull.py:35-66."""
+    return _gather('ib200_pull', inp, grid, bound, interpolation, extrapolate, lambda d: [])
+
+
+def grid_grad(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int):
+    """-> (B, C, *spatial_out, D).  Reference: interpol/pushpull.py:146-172."""
+    return _gather('ib200_grad', inp, grid, bound, interpolation, extrapolate, lambda d: [d])
+
+
+def grid_hess(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int):
+    """-> (B, C, *spatial_out, D, D).  Reference: interpol/pushpull.py:207-233."""
+    return _gather('ib200_hess', inp, grid, bound, interpolation, extrapolate, lambda d: [d, d])
+
+
+def grid_pull_grad_grid(gout, inp, grid, bound, interpolation, extrapolate):
+    """Fused `(grid_grad(inp, grid) * gout.unsqueeze(-1)).sum(1)` -> (B, *spatial_out, D)
+    (the grid branch of interpol/pushpull.py:254-257 without the (B,C,*,D) temporary)."""
+    return _gather('', inp, grid, bound, interpolation, extrapolate, None, gout=gout)
+
+
+def _scatter(fn_name, inp, grid, shape, bound, interpolation, extrapolate, comp=False):
+    _lib.require_cuda(inp, grid)
+    dim = grid.shape[-1]
+    if grid.dim() != dim + 2:
+        raise ValueError('expected grid (B, *spatial, D)')
+    gshape = grid.shape[1:-1]
+    dtype = _common_dtype(inp, grid)
+    grid = grid.to(dtype)
+    if inp is not None:
+        if inp.dim() != dim + 2 + int(comp):
+            raise ValueError('expected inp (B, C, *spatial%s)' % (', D' if comp else ''))
+        inp = inp.to(dtype)
+        if tuple(inp.shape[2:2 + dim]) != tuple(gshape):
+            # iso1.py:150, iso0.py:78
+            raise ValueError('Input and grid should have the same spatial shape')
+        batch = _batch(inp, grid)
+        channels = inp.shape[1]
+    else:
+        batch = grid.shape[0]
+        channels = 1
+    if shape is None:
+        shape = gshape
+    shape = [int(s) for s in shape]
+    if len(shape) != dim:
+        raise ValueError('`shape` should have %d elements' % dim)
+    p = _problem(dim, dtype, grid.device, bound, interpolation, extrapolate, batch, channels,
+                 shape, gshape)
+    _set_grid(p, grid, batch, dim)
+    if inp is not None:
+        _set_img(p, inp, batch, dim, comp)
+    L = _lib.lib()
+    with torch.cuda.device(grid.device):
+        out = torch.empty([batch, channels, *shape], dtype=dtype, device=grid.device)
+        nscratch = L.ib200_scratch_bytes(ctypes.byref(p))
+        scratch = torch.empty([nscratch // 4], dtype=torch.float32, device=grid.device) if nscratch else None
+        s = _lib.stream_ptr(grid.device)
+        if inp is None:
+            st = L.ib200_count(ctypes.byref(p), _lib.ptr(grid), _lib.ptr(out), _lib.ptr(scratch), s)
+        else:
+            st = getattr(L, fn_name)(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid), _lib.ptr(out),
+                                     _lib.ptr(scratch), s)
+    _lib.check(st)
+    return out
+
+
+def grid_push(inp, grid, shape: Optional[List[int]], bound: List[int], interpolation: List[int],
+              extrapolate: int):
+    """(B, C, *spatial_in), (B, *spatial_in, D) -> (B, C, *shape)
+    Reference: interpol/pushpull.py:70-102."""
+    return _scatter('ib200_push', inp, grid, shape, bound, interpolation, extrapolate)
+
+
+def grid_count(grid, shape: Optional[List[int]], bound: List[int], interpolation: List[int],
+               extrapolate: int):
+    """(B, *spatial_in, D) -> (B, 1, *shape).  Reference: interpol/pushpull.py:106-142."""
+    return _scatter('ib200_count', None, grid, shape, bound, interpolation, extrapolate)
+
+
+def grid_pushgrad(inp, grid, shape: List[int], bound: List[int], interpolation: List[int],
+                  extrapolate: int):
+    """(B, C, *spatial_in, D) -> (B, C, *shape).  Reference: interpol/pushpull.py:175-204."""
+    return _scatter('ib200_pushgrad', inp, grid, shape, bound, interpolation, extrapolate, comp=True)
+
+
+# ---------------------------------------------------------------------------
+# backward compositions (interpol/pushpull.py:237-325)
+# ---------------------------------------------------------------------------
+
+def grid_pull_backward(grad, inp, grid, bound, interpolation, extrapolate):
+    """-> (B, C, *spatial_in), (B, *spatial_out, D).  Reference: pushpull.py:237-258."""
+    dim = grid.shape[-1]
+    grad_inp = grad_grid = None
+    if inp.requires_grad:
+        grad_inp = grid_push(grad, grid, inp.shape[-dim:], bound, interpolation, extrapolate)
+    if grid.requires_grad:
+        grad_grid = grid_pull_grad_grid(grad, inp, grid, bound, interpolation, extrapolate)
+    return grad_inp, grad_grid
+
+
+def grid_push_backward(grad, inp, grid, bound, interpolation, extrapolate):
+    """-> (B, C, *spatial_in), (B, *spatial_in, D).  Reference: pushpull.py:262-282."""
+    grad_inp = grad_grid = None
+    if inp.requires_grad:
+        grad_inp = grid_pull(grad, grid, bound, interpolation, extrapolate)
+    if grid.requires_grad:
+        # sum_c grad(grad_vol, grid)[b,c] * inp[b,c]: same fused kernel, roles swapped
+        grad_grid = grid_pull_grad_grid(inp, grad, grid, bound, interpolation, extrapolate)
+    return grad_inp, grad_grid
+
+
+def grid_count_backward(grad, grid, bound, interpolation, extrapolate):
+    """-> (B, *spatial_in, D).  Reference: pushpull.py:286-299."""
+    if grid.requires_grad:
+        ones = torch.ones([1, 1, *([1] * (grid.dim() - 2))], dtype=grad.dtype, device=grad.device)
+        ones = ones.expand([grid.shape[0], grad.shape[1], *grid.shape[1:-1]])
+        return grid_pull_grad_grid(ones, grad, grid, bound, interpolation, extrapolate)
+    return None
+
+
+def grid_grad_backward(grad, inp, grid, bound, interpolation, extrapolate):
+    """grad (B, C, *spatial_out, D) -> (B, C, *spatial_in), (B, *spatial_out, D).
+    Reference: pushpull.py:303-325."""
+    dim = grid.shape[-1]
+    shape = inp.shape[-dim:]
+    grad_inp = grad_grid = None
+    if inp.requires_grad:
+        grad_inp = grid_pushgrad(grad, grid, shape, bound, interpolation, extrapolate)
+    if grid.requires_grad:
+        hess = grid_hess(inp, grid, bound, interpolation, extrapolate)
+        grad_grid = (hess * grad.unsqueeze(-1)).sum(dim=[1, -2])
+    return grad_inp, grad_grid

@@ -202,6 +202,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -277,7 +278,7 @@ def main():
 
     # ---- end-to-end through the public API with pinned host buffers ----------
     vol_h = vol.cpu().pin_memory(); grid_h = grid.cpu().pin_memory()
-    e2e_steps = max(3, min(args.steps, 5))
+    e2e_steps = max(3, min(args.steps, 5)) if not args.no_e2e else 1
 
     def e2e_step():
         o = ib.grid_pull(vol_h, grid_h, interpolation=ORDER, bound=BOUND, extrapolate=EXTRAPOLATE)

@@ -141,9 +141,17 @@ __device__ __forceinline__ bool setup_axis(Axis<R, NODES> &ax, R coord, int orde
             w = R(1) - fabs(x);
             g = x > R(0) ? R(1) : (x < R(0) ? R(-1) : R(0));
         } else {
-            w = spline_weight<R>(order, x);
-            if (NEED >= 1) g = spline_grad<R>(order, x);
-            if (NEED >= 2) h = spline_hess<R>(order, x);
+            if (sizeof(R) == 4 && order >= 6) {
+                // degree-6/7 Horner forms cancel ~2 digits in float32 (the reference's own
+                // float32 noise at order 7 is 1-2e-5): evaluate in double
+                w = (R)spline_weight<double>(order, (double)x);
+                if (NEED >= 1) g = (R)spline_grad<double>(order, (double)x);
+                if (NEED >= 2) h = (R)spline_hess<double>(order, (double)x);
+            } else {
+                w = spline_weight<R>(order, x);
+                if (NEED >= 1) g = spline_grad<R>(order, x);
+                if (NEED >= 2) h = spline_hess<R>(order, x);
+            }
         }
         ax.w[k] = w * s;
         if (NEED >= 1) ax.g[k] = g * s;

@@ -28,7 +28,7 @@ ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 # the environment may export CC/CXX pointing at a toolchain without the system
 # headers nvcc expects; pin the system g++
 CCBIN = ['-ccbin', os.environ.get('IB200_CXX', '/usr/bin/g++')]
-COMMON = ['-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
+COMMON = (['-DIB200_TUNE'] if os.environ.get('IB200_TUNE') else []) + ['-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
           '--expt-relaxed-constexpr']
 
 # storage type -> (C++ type, accumulator for scatter, statically unrolled orders)

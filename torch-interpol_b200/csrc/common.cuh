@@ -105,7 +105,7 @@ IB200_DECL_LAUNCHERS(bf16)
 int launch_coeff(void *data, int dtype, i64 outer, i64 n, i64 inner, int bound, int order,
                  cudaStream_t stream);
 // tiled fast paths: return 1 when they handled the call, 0 when not applicable, <0 on error
-int try_pull_tiled(const KParams &kp, int dtype, const void *vol, const void *grid, void *out,
+int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out,
                    cudaStream_t stream);
 int try_push_tiled(int op, const KParams &kp, int dtype, const void *img, const void *grid,
                    void *out, cudaStream_t stream);

@@ -1,0 +1,208 @@
+// Helpers shared by the shared-memory tiled pull / push kernels (3-D, compile-
+// time isotropic order): fixed node->piece weight evaluation, tile geometry,
+// CTA-wide bounding-box reduction, boundary tables.
+#pragma once
+#include "support.cuh"
+
+namespace ib200 {
+
+// Weights of the ORDER+1 nodes from t = g - i0, with the polynomial piece of
+// every node fixed at compile time: node k sits at signed distance x = t - k
+// and t lies in [(ORDER-1)/2, (ORDER+1)/2] so |x| falls in a known knot
+// interval (B-splines are continuous, so the closed end does not matter).
+// Same polynomials as splines.cuh / interpol/splines.py:30-80.
+template <int ORDER>
+__device__ __forceinline__ void fast_weights(float t, float (&w)[ORDER + 1]) {
+    if constexpr (ORDER == 0) {
+        w[0] = 1.f;
+    } else if constexpr (ORDER == 1) {
+        w[0] = 1.f - t; w[1] = t;
+    } else if constexpr (ORDER == 2) {
+        // t in [0.5, 1.5]: nodes at |x| = t (outer), |t-1| (inner), 2-t (outer)
+        const float a = 1.5f - t, c = t - 0.5f, x1 = t - 1.f;
+        w[0] = 0.5f * a * a;
+        w[1] = 0.75f - x1 * x1;
+        w[2] = 0.5f * c * c;
+    } else if constexpr (ORDER == 3) {
+        // t in [1, 2]: |x| = t (outer), t-1 (inner), 2-t (inner), 3-t (outer)
+        const float a = 2.f - t, x1 = t - 1.f;
+        w[0] = a * a * a * (1.f / 6.f);
+        w[1] = (x1 * x1 * (x1 - 2.f) * 3.f + 4.f) * (1.f / 6.f);
+        w[2] = (a * a * (a - 2.f) * 3.f + 4.f) * (1.f / 6.f);
+        w[3] = x1 * x1 * x1 * (1.f / 6.f);
+    } else {
+#pragma unroll
+        for (int k = 0; k <= ORDER; ++k) {
+            if (ORDER >= 6) w[k] = (float)spline_weight<double>(ORDER, (double)(t - (float)k));
+            else w[k] = spline_weight<float>(ORDER, t - (float)k);
+        }
+    }
+}
+
+// largest value a single node weight can take (bounds the splat contributions)
+__host__ __device__ constexpr float max_weight(int order) {
+    return order <= 1 ? 1.f : order == 2 ? 0.75f : order == 3 ? (2.f / 3.f) : order == 4 ? (115.f / 192.f)
+         : order == 5 ? 0.55f : order == 6 ? (5887.f / 11520.f) : (151.f / 315.f);
+}
+
+// first derivative of the node weights, same fixed node->piece assignment
+// (interpol/splines.py:90-139; order 1 uses the iso1 closed form -1/+1)
+template <int ORDER>
+__device__ __forceinline__ void fast_dweights(float t, float (&g)[ORDER + 1]) {
+    if constexpr (ORDER == 0) {
+        g[0] = 0.f;
+    } else if constexpr (ORDER == 1) {
+        g[0] = -1.f; g[1] = 1.f;
+    } else if constexpr (ORDER == 2) {
+        g[0] = t - 1.5f; g[1] = -2.f * (t - 1.f); g[2] = t - 0.5f;
+    } else if constexpr (ORDER == 3) {
+        const float a = 2.f - t, x1 = t - 1.f;
+        g[0] = -0.5f * a * a;
+        g[1] = x1 * (1.5f * x1 - 2.f);
+        g[2] = -a * (1.5f * a - 2.f);
+        g[3] = 0.5f * x1 * x1;
+    } else {
+#pragma unroll
+        for (int k = 0; k <= ORDER; ++k) {
+            if (ORDER >= 6) g[k] = (float)spline_grad<double>(ORDER, (double)(t - (float)k));
+            else g[k] = spline_grad<float>(ORDER, t - (float)k);
+        }
+    }
+}
+
+struct TileGeom {
+    int lo[3];      // unfolded source coordinate of tile element (0,0,0)
+    int ext[3];     // extents
+    int sz, sxy;    // strides (elements) of the y and x axes inside the tile
+    int fits;       // the box fits in shared memory
+    int plain;      // the box lies strictly inside the volume: no fold, no sign
+    int vpr;        // 16-byte vectors per staged row
+    unsigned inv_vpr, inv_e1, inv_cpr;   // ceil(2^32 / d) for d = vpr, ext[1], sz/32
+};
+
+// exact q / d for q * d < 2^32 with inv = floor(2^32 / d) + 1
+__device__ __forceinline__ int fast_div(int q, unsigned inv) { return inv ? (int)__umulhi((unsigned)q, inv) : q; }
+__host__ __device__ __forceinline__ unsigned make_inv(int d) { return d <= 1 ? 0u : (unsigned)(0x100000000ULL / (unsigned)d) + 1u; }
+
+constexpr int kMaxExt = 160;      // longest tile edge the boundary tables hold
+constexpr int kIntMax = 0x7fffffff;
+constexpr int kIntMin = -0x7fffffff - 1;
+
+struct PlaneBox { int mn[3], mx[3]; };   // support starts of one x-plane of the tile
+
+// Geometry of the union of planes [p0, p1).  Rows are padded to a multiple of 32
+// words: the bank of a tap then depends on its z only, so lanes whose supports
+// sit on different (x, y) rows never collide; the z origin is aligned to 4 words
+// so rows can be staged / flushed 16 bytes at a time.
+template <int ORDER>
+__device__ __forceinline__ TileGeom make_geom(const KParams &kp, const PlaneBox *pb, int p0, int p1, int cap) {
+    TileGeom g;
+    bool any = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int a = kIntMax, b = kIntMin;
+        for (int p = p0; p < p1; ++p) { a = min(a, pb[p].mn[d]); b = max(b, pb[p].mx[d]); }
+        if (a > b) { any = false; a = 0; b = 0; }
+        if (d == 2) a &= ~3;
+        g.lo[d] = a;
+        const long long e = (long long)b - a + 1 + ORDER;
+        g.ext[d] = (int)(e > 0x3fffffff ? 0x3fffffff : e);
+    }
+    g.sz = (int)(((long long)g.ext[2] + 31) & ~31LL);
+    g.sxy = g.sz * (g.ext[1] < 4096 ? g.ext[1] : 4096);
+    const long long vol = (long long)g.sz * g.ext[1] * g.ext[0];
+    g.fits = any && g.ext[0] <= kMaxExt && g.ext[1] <= kMaxExt && g.ext[2] <= kMaxExt && vol <= cap;
+    if (!any) { g.fits = 1; g.ext[0] = g.ext[1] = g.ext[2] = 0; g.sz = 32; g.sxy = 0; }
+    bool plain = g.fits && any;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int lo_ok = (kp.bound[d] == IB200_BOUND_DST1) ? 1 : 0;     // dst1 zeroes voxel 0 (Q1)
+        const int hi = g.lo[d] + (d == 2 ? ((g.ext[2] + 3) & ~3) : g.ext[d]) - 1;
+        plain = plain && g.lo[d] >= lo_ok && hi <= kp.vol_n[d] - 1;
+    }
+    g.plain = plain;
+    g.vpr = (g.ext[2] + 3) >> 2;
+    g.inv_vpr = make_inv(g.vpr);
+    g.inv_e1 = make_inv(g.ext[1]);
+    g.inv_cpr = make_inv(g.sz >> 5);
+    return g;
+}
+
+// Plan for a tile: `whole` is the box of the entire tile (warp partials in
+// red[NW][6]).  When it fits the tile is one group (the common case); otherwise
+// `per_plane()` is asked to fill red[TX][NW][6] with per-x-plane partials and the
+// tile is split into 2, 4, ... groups of planes until every group fits.
+template <int ORDER, int TX, int NT, typename F>
+__device__ __forceinline__ void plan_tile(const KParams &kp, int *red, PlaneBox *pb, TileGeom *geoms,
+                                          int *nsub, int cap, F per_plane) {
+    constexpr int NW = NT / 32;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PlaneBox b;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int a = kIntMax, c = kIntMin;
+            for (int w = 0; w < NW; ++w) { a = min(a, red[w * 6 + 2 * d]); c = max(c, red[w * 6 + 2 * d + 1]); }
+            b.mn[d] = a; b.mx[d] = c;
+        }
+        pb[0] = b;
+        geoms[0] = make_geom<ORDER>(kp, pb, 0, 1, cap);
+        *nsub = geoms[0].fits ? 1 : 0;
+    }
+    __syncthreads();
+    if (*nsub == 1) return;
+    // ---- rare: the whole-tile box does not fit -> per-plane boxes ------------
+    per_plane();
+    __syncthreads();
+    if (threadIdx.x < TX) {
+        PlaneBox b;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int a = kIntMax, c = kIntMin;
+            for (int w = 0; w < NW; ++w) {
+                a = min(a, red[(threadIdx.x * NW + w) * 6 + 2 * d]);
+                c = max(c, red[(threadIdx.x * NW + w) * 6 + 2 * d + 1]);
+            }
+            b.mn[d] = a; b.mx[d] = c;
+        }
+        pb[threadIdx.x] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ns = 2;
+        for (; ns <= TX; ns *= 2) {
+            bool ok = true;
+            const int per = TX / ns;
+            for (int s = 0; s < ns; ++s) {
+                geoms[s] = make_geom<ORDER>(kp, pb, s * per, (s + 1) * per, cap);
+                ok = ok && geoms[s].fits;
+            }
+            if (ok || ns == TX) break;
+        }
+        *nsub = ns;
+    }
+    __syncthreads();
+}
+
+// idx_tab[d][e] = bound_index(lo_d + e) * stride_d ; sgn_tab[d][e] = bound_sign(lo_d + e)
+template <int NT>
+__device__ __forceinline__ void build_tables(const KParams &kp, const TileGeom &g, int *idx_tab, float *sgn_tab) {
+    for (int q = threadIdx.x; q < 3 * kMaxExt; q += NT) {
+        const int d = q / kMaxExt, e = q - d * kMaxExt;
+        if (e < g.ext[d]) {
+            const int src = g.lo[d] + e;
+            idx_tab[q] = bound_index<int>(kp.bound[d], src, kp.vol_n[d]) * (int)kp.vol_s[d];
+            sgn_tab[q] = (float)bound_sign<int>(kp.bound[d], src, kp.vol_n[d]);
+        }
+    }
+}
+
+// ---- cp.async helpers (LDGSTS: global -> shared without register staging) ----
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+}  // namespace ib200

@@ -165,9 +165,15 @@ static int run_scatter(int op, const ib200_problem *p, const void *img, const vo
     DeviceGuard guard(p->device);
     if (!guard.ok) return IB200_ERR_CUDA - (int)cudaErrorInvalidDevice;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!(p->flags & IB200_FLAG_NO_TILES)) {
-        st = try_push_tiled(op, kp, p->dtype, img, grid, out, s);
-        if (st != 0) return st < 0 ? st : IB200_OK;
+    if (!(p->flags & IB200_FLAG_NO_TILES) && push_tiled_applicable(op, kp, p->dtype)) {
+        const bool half = p->dtype != IB200_F32;
+        if (half && !scratch) return IB200_ERR_SCRATCH;
+        void *acc = half ? scratch : out;
+        const i64 n = kp.batch * kp.channels * kp.vol_total;
+        IB200_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(float), s));
+        st = try_push_tiled(op, kp, p->dtype, img, grid, acc, s);
+        if (st < 0) return st;
+        if (st > 0) return half ? convert_from_f32(p->dtype, acc, out, n, s) : IB200_OK;
     }
     switch (p->dtype) {
     case IB200_F32: return launch_scatter_f32(op, kp, img, grid, out, scratch, s);

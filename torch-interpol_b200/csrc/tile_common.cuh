@@ -206,3 +206,99 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 }  // namespace ib200
+
+namespace ib200 {
+
+// ---- shared phases of the tiled kernels -----------------------------------
+
+// Phase 1: stage the grid coordinates of a TX x TY x TZ tile (TX*TY rows of TZ*3
+// values) into shared memory; a warp copies one row per pass, 16 bytes per lane.
+template <typename T, int TX, int TY, int TZ, int NT>
+__device__ __forceinline__ void stage_grid_tile(const KParams &kp, const T *gridb, T *gtile, int x0, int y0, int z0,
+                                                int nzv, int vec_ok) {
+    constexpr int ROWV = TZ * 3 * (int)sizeof(T) / 16;               // 16-byte vectors per row (<= 32)
+    constexpr int EPV = 16 / (int)sizeof(T);
+    constexpr int NW = NT / 32;
+    static_assert(ROWV <= 32, "one warp stages one row of grid coordinates per pass");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool vec = vec_ok && nzv == TZ;
+#pragma unroll
+    for (int rw = warp; rw < TX * TY; rw += NW) {                    // warp-uniform row
+        const int lx = rw / TY, lyy = rw - lx * TY;
+        if (lane < ROWV && x0 + lx < kp.pts_n[0] && y0 + lyy < kp.pts_n[1]) {
+            const int off = (((x0 + lx) * kp.pts_n[1] + (y0 + lyy)) * kp.pts_n[2] + z0) * 3 + lane * EPV;
+            T *sdst = gtile + rw * (TZ * 3) + lane * EPV;
+            if (vec) {
+                cp_async16(sdst, gridb + off);
+            } else {
+                for (int e = 0; e < EPV; ++e)
+                    if (lane * EPV + e < nzv * 3) sdst[e] = gridb[off + e];
+            }
+        }
+    }
+}
+
+// support start of the point of this thread in plane p: 0 inactive, 1 ok, 2 absurd
+template <typename T, int ORDER, int NT>
+__device__ __forceinline__ int support_start(const KParams &kp, const T *gtile, int p, bool in_tile, int (&i0)[3]) {
+    if (!in_tile) return 0;
+    const T *g = gtile + (p * NT + threadIdx.x) * 3;
+    const float c[3] = {(float)g[0], (float)g[1], (float)g[2]};
+    // nd.py:45: support start floor(g - (order-1)/2)
+    const float f0 = floorf(c[0] - 0.5f * (ORDER - 1)), f1 = floorf(c[1] - 0.5f * (ORDER - 1)),
+                f2 = floorf(c[2] - 0.5f * (ORDER - 1));
+    if (!(inbounds<float, 3>(kp, c) && fabsf(f0) < 4e18f && fabsf(f1) < 4e18f && fabsf(f2) < 4e18f)) return 0;
+    if (!(fabsf(f0) < 1e9f && fabsf(f1) < 1e9f && fabsf(f2) < 1e9f)) return 2;
+    i0[0] = (int)f0; i0[1] = (int)f1; i0[2] = (int)f2;
+    return 1;
+}
+
+// Phase 2: bounding boxes -> plan (whole tile first, per-plane split when it does not fit)
+template <typename T, int ORDER, int TX, int NT>
+__device__ __forceinline__ void plan_from_coords(const KParams &kp, const T *gtile, bool col_ok, int x0, int *red,
+                                                 PlaneBox *pb, TileGeom *geoms, int *nsub, int cap) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        int mn[3] = {kIntMax, kIntMax, kIntMax}, mx[3] = {kIntMin, kIntMin, kIntMin};
+#pragma unroll
+        for (int p = 0; p < TX; ++p) {
+            int i0[3];
+            const int st = support_start<T, ORDER, NT>(kp, gtile, p, col_ok && x0 + p < kp.pts_n[0], i0);
+            if (st == 1) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], i0[d]); mx[d] = max(mx[d], i0[d]); }
+            } else if (st == 2) {          // finite but absurd coordinate: the box cannot fit
+                mn[0] = -0x40000000; mx[0] = 0x40000000;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int a = __reduce_min_sync(0xffffffffu, mn[d]);
+            const int c = __reduce_max_sync(0xffffffffu, mx[d]);
+            if (lane == 0) { red[warp * 6 + 2 * d] = a; red[warp * 6 + 2 * d + 1] = c; }
+        }
+    }
+    plan_tile<ORDER, TX, NT>(kp, red, pb, geoms, nsub, cap, [&]() {
+#pragma unroll 1
+        for (int p = 0; p < TX; ++p) {
+            int mn[3] = {kIntMax, kIntMax, kIntMax}, mx[3] = {kIntMin, kIntMin, kIntMin};
+            int i0[3];
+            const int st = support_start<T, ORDER, NT>(kp, gtile, p, col_ok && x0 + p < kp.pts_n[0], i0);
+            if (st == 1) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { mn[d] = i0[d]; mx[d] = i0[d]; }
+            } else if (st == 2) {
+                mn[0] = -0x40000000; mx[0] = 0x40000000; mn[1] = mx[1] = mn[2] = mx[2] = 0;
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int a = __reduce_min_sync(0xffffffffu, mn[d]);
+                const int c = __reduce_max_sync(0xffffffffu, mx[d]);
+                if (lane == 0) { red[(p * NW + warp) * 6 + 2 * d] = a; red[(p * NW + warp) * 6 + 2 * d + 1] = c; }
+            }
+        }
+    });
+}
+
+}  // namespace ib200

@@ -44,11 +44,9 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
     int *idx_tab = reinterpret_cast<int *>(reinterpret_cast<float *>(gtile) + (NPT * 3 * sizeof(T)) / 4);
     float *sgn_tab = reinterpret_cast<float *>(idx_tab + 3 * kMaxExt);
     int *red = reinterpret_cast<int *>(sgn_tab + 3 * kMaxExt);          // [TX][NW][6]
-    PlaneBox *pb = reinterpret_cast<PlaneBox *>(red + TX * NW * 6);     // [TX]
+    PlaneBox *pb = reinterpret_cast<PlaneBox *>(red + TX * NW * 8);     // [TX]
     TileGeom *geoms = reinterpret_cast<TileGeom *>(pb + TX);            // [TX]
     int *nsub_p = reinterpret_cast<int *>(geoms + TX);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
     // ---- which tile ------------------------------------------------------
     const int ntx = (kp.pts_n[0] + TX - 1) / TX, nty = (kp.pts_n[1] + TY - 1) / TY, ntz = (kp.pts_n[2] + TZ - 1) / TZ;
     int tid = blockIdx.x;
@@ -61,85 +59,11 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
     const int lz = threadIdx.x % TZ, ly = threadIdx.x / TZ;
     const bool col_ok = (y0 + ly < kp.pts_n[1]) && (lz < nzv);
 
-    // ---- 1. stage the grid coordinates: TX*TY rows of TZ*3 values -----------
-    // (element offsets fit in 32 bits: the host checks pts_total * 3 < 2^31)
-    const T *gridb = grid + b * kp.grid_sb;
-    {
-        constexpr int ROWV = TZ * 3 * (int)sizeof(T) / 16;               // 16-byte vectors per row (<= 32)
-        constexpr int EPV = 16 / (int)sizeof(T);
-        static_assert(ROWV <= 32, "one warp stages one row of grid coordinates per pass");
-        const bool vec = vec_ok && nzv == TZ;
-#pragma unroll
-        for (int rw = warp; rw < TX * TY; rw += NW) {                    // warp-uniform row
-            const int lx = rw / TY, lyy = rw - lx * TY;
-            if (lane < ROWV && x0 + lx < kp.pts_n[0] && y0 + lyy < kp.pts_n[1]) {
-                const int off = (((x0 + lx) * kp.pts_n[1] + (y0 + lyy)) * kp.pts_n[2] + z0) * 3 + lane * EPV;
-                T *sdst = gtile + rw * (TZ * 3) + lane * EPV;
-                if (vec) {
-                    cp_async16(sdst, gridb + off);
-                } else {
-                    for (int e = 0; e < EPV; ++e)
-                        if (lane * EPV + e < nzv * 3) sdst[e] = gridb[off + e];
-                }
-            }
-        }
-        cp_async_wait_all();
-        __syncthreads();
-    }
-
-    // ---- 2. bounding box of the spline supports -> plan -----------------------
-    auto support_start = [&](int p, int (&i0)[3]) -> int {     // 0: inactive, 1: ok, 2: absurd
-        if (!(col_ok && x0 + p < kp.pts_n[0])) return 0;
-        const T *g = gtile + (p * NT + threadIdx.x) * 3;
-        const float c[3] = {(float)g[0], (float)g[1], (float)g[2]};
-        // nd.py:45: support start floor(g - (order-1)/2)
-        const float f0 = floorf(c[0] - 0.5f * (ORDER - 1)), f1 = floorf(c[1] - 0.5f * (ORDER - 1)),
-                    f2 = floorf(c[2] - 0.5f * (ORDER - 1));
-        if (!(inbounds<float, 3>(kp, c) && fabsf(f0) < 4e18f && fabsf(f1) < 4e18f && fabsf(f2) < 4e18f)) return 0;
-        if (!(fabsf(f0) < 1e9f && fabsf(f1) < 1e9f && fabsf(f2) < 1e9f)) return 2;
-        i0[0] = (int)f0; i0[1] = (int)f1; i0[2] = (int)f2;
-        return 1;
-    };
-    {
-        int mn[3] = {kIntMax, kIntMax, kIntMax}, mx[3] = {kIntMin, kIntMin, kIntMin};
-#pragma unroll
-        for (int p = 0; p < TX; ++p) {
-            int i0[3];
-            const int st = support_start(p, i0);
-            if (st == 1) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], i0[d]); mx[d] = max(mx[d], i0[d]); }
-            } else if (st == 2) {          // finite but absurd coordinate: the box cannot fit
-                mn[0] = -0x40000000; mx[0] = 0x40000000;
-            }
-        }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int a = __reduce_min_sync(0xffffffffu, mn[d]);
-            const int c = __reduce_max_sync(0xffffffffu, mx[d]);
-            if (lane == 0) { red[warp * 6 + 2 * d] = a; red[warp * 6 + 2 * d + 1] = c; }
-        }
-    }
-    plan_tile<ORDER, TX, NT>(kp, red, pb, geoms, nsub_p, cap, [&]() {
-#pragma unroll 1
-        for (int p = 0; p < TX; ++p) {
-            int mn[3] = {kIntMax, kIntMax, kIntMax}, mx[3] = {kIntMin, kIntMin, kIntMin};
-            int i0[3];
-            const int st = support_start(p, i0);
-            if (st == 1) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) { mn[d] = i0[d]; mx[d] = i0[d]; }
-            } else if (st == 2) {
-                mn[0] = -0x40000000; mx[0] = 0x40000000; mn[1] = mx[1] = mn[2] = mx[2] = 0;
-            }
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const int a = __reduce_min_sync(0xffffffffu, mn[d]);
-                const int c = __reduce_max_sync(0xffffffffu, mx[d]);
-                if (lane == 0) { red[(p * NW + warp) * 6 + 2 * d] = a; red[(p * NW + warp) * 6 + 2 * d + 1] = c; }
-            }
-        }
-    });
+    // ---- 1. + 2. grid coordinates, bounding boxes, plan (tile_common.cuh) ------
+    stage_grid_tile<T, TX, TY, TZ, NT>(kp, grid + b * kp.grid_sb, gtile, x0, y0, z0, nzv, vec_ok);
+    cp_async_wait_all();
+    __syncthreads();
+    plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap);
     const int nsub = *nsub_p;
     const int per = TX / nsub;
 
@@ -286,7 +210,7 @@ template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MIN
 static int launch_pull_tile_cfg(const KParams &kp, const void *vol, const void *grid, void *out, cudaStream_t stream,
                                 size_t smem_total) {
     const size_t fixed = (size_t)TX * TY * TZ * 3 * sizeof(T) + 3 * kMaxExt * (sizeof(int) + sizeof(float)) +
-                         TX * (NT / 32) * 6 * sizeof(int) + TX * (sizeof(PlaneBox) + sizeof(TileGeom)) + 32;
+                         TX * (NT / 32) * 8 * sizeof(int) + TX * (sizeof(PlaneBox) + sizeof(TileGeom)) + 32;
     const int cap = (int)((smem_total - fixed) / sizeof(float)) & ~31;
     const i64 ntiles = kp.batch * ((kp.pts_n[0] + TX - 1) / TX) * ((kp.pts_n[1] + TY - 1) / TY) * ((kp.pts_n[2] + TZ - 1) / TZ);
     if (ntiles == 0) return 1;

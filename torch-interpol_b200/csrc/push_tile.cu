@@ -49,11 +49,12 @@ push_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img
     int *idx_tab = reinterpret_cast<int *>(reinterpret_cast<float *>(gtile) + (NPT * 3 * sizeof(T)) / 4);
     float *sgn_tab = reinterpret_cast<float *>(idx_tab + 3 * kMaxExt);
     int *red = reinterpret_cast<int *>(sgn_tab + 3 * kMaxExt);          // [TX][NW][6]
-    PlaneBox *pb = reinterpret_cast<PlaneBox *>(red + TX * NW * 6);     // [TX]
+    PlaneBox *pb = reinterpret_cast<PlaneBox *>(red + TX * NW * 8);     // [TX]
     TileGeom *geoms = reinterpret_cast<TileGeom *>(pb + TX);            // [TX]
     int *nsub_p = reinterpret_cast<int *>(geoms + TX);
     int *hist = nsub_p + 4;                                             // [kHist]
     float *scal = reinterpret_cast<float *>(hist + kHist);              // [4] vmax, scale, 1/scale
+    float *vals = scal + 4;                                             // [NPT] source values of the current channel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- which tile ------------------------------------------------------
@@ -68,11 +69,32 @@ push_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img
     const int lz = threadIdx.x % TZ, ly = threadIdx.x / TZ;
     const bool col_ok = (y0 + ly < kp.pts_n[1]) && (lz < nzv);
 
-    // ---- 1. + 2. grid coordinates, bounding boxes, plan ------------------------
+    // ---- 1. + 2. grid coordinates (+ values of channel 0), bounding boxes, plan ----
     stage_grid_tile<T, TX, TY, TZ, NT>(kp, grid + b * kp.grid_sb, gtile, x0, y0, z0, nzv, vec_ok);
+    auto stage_values = [&](i64 c) {       // vals[p * NT + tid] = img[b, c, x0 + p, y0 + ly, z0 + lz]
+        if (COUNT) return;
+        const T *src = img + b * kp.img_sb + c * kp.img_sc;
+#pragma unroll
+        for (int p = 0; p < TX; ++p) {
+            float v = 0.f;
+            if (col_ok && x0 + p < kp.pts_n[0])
+                v = Traits<T>::load(src + (((x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lz)));
+            vals[p * NT + threadIdx.x] = v;
+        }
+    };
+    auto local_vmax = [&]() -> float {     // max |value| over this thread's points (own slots: no barrier needed)
+        if (COUNT) return 1.f;
+        float m = 0.f;
+#pragma unroll
+        for (int p = 0; p < TX; ++p) m = fmaxf(m, fabsf(vals[p * NT + threadIdx.x]));
+        return m < 3e38f ? m : 3e38f;      // inf / NaN values: garbage in, garbage out
+    };
+    stage_values(0);
     cp_async_wait_all();
     __syncthreads();
-    plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap);
+    plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap, local_vmax());
+    float vmax_tile = __int_as_float(red[kExtraSlot]);
+    i64 cur_c = 0;                         // channel whose values are staged in `vals`
     const int nsub = *nsub_p;
     const int per = TX / nsub;
     const float w3 = max_weight(ORDER) * max_weight(ORDER) * max_weight(ORDER);
@@ -88,11 +110,19 @@ push_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img
         for (i64 c = 0; c < kp.channels; ++c) {
             const T *src = COUNT ? nullptr : img + b * kp.img_sb + c * kp.img_sc;
             float *dst = out + (b * kp.channels + c) * kp.vol_total;
-            auto value = [&](int p) -> float {
-                if (COUNT) return 1.f;
-                const int r = ((x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lz);
-                return Traits<T>::load(src + r);
-            };
+            auto value = [&](int p) -> float { return COUNT ? 1.f : vals[p * NT + threadIdx.x]; };
+            if (c != cur_c) {              // another channel: restage the values, redo the maximum
+                cur_c = c;
+                __syncthreads();
+                stage_values(c);
+                const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(local_vmax()));
+                if (lane == 0) red[warp] = (int)m;
+                __syncthreads();
+                unsigned mm = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) mm = max(mm, (unsigned)red[w]);
+                vmax_tile = __uint_as_float(mm);
+            }
             if (tiled) {
                 // ---- a. zero the accumulators and the histogram, find max |value| -----
                 __syncthreads();                                        // previous flush done
@@ -102,25 +132,7 @@ push_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img
                     for (int q = threadIdx.x; q < n4; q += NT) a4[q] = make_int4(0, 0, 0, 0);
                     for (int q = threadIdx.x; q < nc0 * nc1 * nc2; q += NT) hist[q] = 0;
                 }
-                float vmax = 0.f;
-                if (COUNT) {
-                    vmax = 1.f;
-                } else {
-#pragma unroll 1
-                    for (int p = s * per; p < (s + 1) * per; ++p) {
-                        int i0[3];
-                        if (support_start<T, ORDER, NT>(kp, gtile, p, col_ok && x0 + p < kp.pts_n[0], i0) == 1)
-                            vmax = fmaxf(vmax, fabsf(value(p)));
-                    }
-                    if (!(vmax < 3e38f)) vmax = 3e38f;                  // inf / NaN values: garbage in, garbage out
-                    unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-                    if (lane == 0) red[warp] = (int)m;
-                    __syncthreads();
-                    unsigned mm = 0;
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) mm = max(mm, (unsigned)red[w]);
-                    vmax = __uint_as_float(mm);
-                }
+                const float vmax = vmax_tile;   // max |value| over the tile (>= the group's: still a bound)
                 __syncthreads();                                        // zeros visible, red reusable
                 if (vmax > 0.f) {
                     // ---- b. rigorous bound on any accumulator -> power-of-two scale --------
@@ -267,8 +279,8 @@ template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MIN
 static int launch_push_tile_cfg(const KParams &kp, const void *img, const void *grid, float *out, cudaStream_t stream,
                                 size_t smem_total) {
     const size_t fixed = (size_t)TX * TY * TZ * 3 * sizeof(T) + 3 * kMaxExt * (sizeof(int) + sizeof(float)) +
-                         TX * (NT / 32) * 6 * sizeof(int) + TX * (sizeof(PlaneBox) + sizeof(TileGeom)) +
-                         (kHist + 8) * sizeof(int) + 64;
+                         TX * (NT / 32) * 8 * sizeof(int) + TX * (sizeof(PlaneBox) + sizeof(TileGeom)) +
+                         (kHist + 8) * sizeof(int) + (size_t)TX * TY * TZ * sizeof(float) + 64;
     const int cap = (int)((smem_total - fixed) / sizeof(int)) & ~31;
     const i64 ntiles = kp.batch * ((kp.pts_n[0] + TX - 1) / TX) * ((kp.pts_n[1] + TY - 1) / TY) * ((kp.pts_n[2] + TZ - 1) / TZ);
     if (ntiles == 0) return 1;

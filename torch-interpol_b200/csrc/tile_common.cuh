@@ -128,62 +128,6 @@ __device__ __forceinline__ TileGeom make_geom(const KParams &kp, const PlaneBox 
     return g;
 }
 
-// Plan for a tile: `whole` is the box of the entire tile (warp partials in
-// red[NW][6]).  When it fits the tile is one group (the common case); otherwise
-// `per_plane()` is asked to fill red[TX][NW][6] with per-x-plane partials and the
-// tile is split into 2, 4, ... groups of planes until every group fits.
-template <int ORDER, int TX, int NT, typename F>
-__device__ __forceinline__ void plan_tile(const KParams &kp, int *red, PlaneBox *pb, TileGeom *geoms,
-                                          int *nsub, int cap, F per_plane) {
-    constexpr int NW = NT / 32;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        PlaneBox b;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            int a = kIntMax, c = kIntMin;
-            for (int w = 0; w < NW; ++w) { a = min(a, red[w * 6 + 2 * d]); c = max(c, red[w * 6 + 2 * d + 1]); }
-            b.mn[d] = a; b.mx[d] = c;
-        }
-        pb[0] = b;
-        geoms[0] = make_geom<ORDER>(kp, pb, 0, 1, cap);
-        *nsub = geoms[0].fits ? 1 : 0;
-    }
-    __syncthreads();
-    if (*nsub == 1) return;
-    // ---- rare: the whole-tile box does not fit -> per-plane boxes ------------
-    per_plane();
-    __syncthreads();
-    if (threadIdx.x < TX) {
-        PlaneBox b;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            int a = kIntMax, c = kIntMin;
-            for (int w = 0; w < NW; ++w) {
-                a = min(a, red[(threadIdx.x * NW + w) * 6 + 2 * d]);
-                c = max(c, red[(threadIdx.x * NW + w) * 6 + 2 * d + 1]);
-            }
-            b.mn[d] = a; b.mx[d] = c;
-        }
-        pb[threadIdx.x] = b;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int ns = 2;
-        for (; ns <= TX; ns *= 2) {
-            bool ok = true;
-            const int per = TX / ns;
-            for (int s = 0; s < ns; ++s) {
-                geoms[s] = make_geom<ORDER>(kp, pb, s * per, (s + 1) * per, cap);
-                ok = ok && geoms[s].fits;
-            }
-            if (ok || ns == TX) break;
-        }
-        *nsub = ns;
-    }
-    __syncthreads();
-}
-
 // idx_tab[d][e] = bound_index(lo_d + e) * stride_d ; sgn_tab[d][e] = bound_sign(lo_d + e)
 template <int NT>
 __device__ __forceinline__ void build_tables(const KParams &kp, const TileGeom &g, int *idx_tab, float *sgn_tab) {
@@ -253,52 +197,117 @@ __device__ __forceinline__ int support_start(const KParams &kp, const T *gtile, 
     return 1;
 }
 
-// Phase 2: bounding boxes -> plan (whole tile first, per-plane split when it does not fit)
+// order-preserving float <-> int key (so that integer REDUX min/max works on floats)
+__device__ __forceinline__ int fkey(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+// floor(c - (ORDER-1)/2) as a saturated int
+template <int ORDER>
+__device__ __forceinline__ int start_of(float c) {
+    const float f = floorf(c - 0.5f * (ORDER - 1));
+    return (int)fminf(fmaxf(f, -1.5e9f), 1.5e9f);
+}
+
+// Phase 2: bounding boxes -> plan (whole tile first, per-plane split when it does not fit).
+// The box is reduced on the raw coordinates (floor is monotone, so the floor of the
+// min / max coordinate is the min / max support start); NaNs drop out of fminf/fmaxf,
+// infinities make the box infinite and send the tile to the global fallback.
+// `extra` is an additional non-negative per-thread value reduced with max (|value| for push);
+// its CTA-wide maximum is left in red[kExtraSlot] as raw float bits.
+constexpr int kExtraSlot = 6;
 template <typename T, int ORDER, int TX, int NT>
 __device__ __forceinline__ void plan_from_coords(const KParams &kp, const T *gtile, bool col_ok, int x0, int *red,
-                                                 PlaneBox *pb, TileGeom *geoms, int *nsub, int cap) {
+                                                 PlaneBox *pb, TileGeom *geoms, int *nsub, int cap, float extra = 0.f) {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        int mn[3] = {kIntMax, kIntMax, kIntMax}, mx[3] = {kIntMin, kIntMin, kIntMin};
+    const bool masked = kp.extrapolate != 1;
+    auto reduce_planes = [&](int p0, int p1, int slot) {
+        float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
+        for (int p = p0; p < p1; ++p) {
+            if (col_ok && x0 + p < kp.pts_n[0]) {
+                const T *g = gtile + (p * NT + threadIdx.x) * 3;
+                const float c[3] = {(float)g[0], (float)g[1], (float)g[2]};
+                if (!masked || inbounds<float, 3>(kp, c)) {
 #pragma unroll
-        for (int p = 0; p < TX; ++p) {
-            int i0[3];
-            const int st = support_start<T, ORDER, NT>(kp, gtile, p, col_ok && x0 + p < kp.pts_n[0], i0);
-            if (st == 1) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], i0[d]); mx[d] = max(mx[d], i0[d]); }
-            } else if (st == 2) {          // finite but absurd coordinate: the box cannot fit
-                mn[0] = -0x40000000; mx[0] = 0x40000000;
+                    for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], c[d]); mx[d] = fmaxf(mx[d], c[d]); }
+                }
             }
         }
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            const int a = __reduce_min_sync(0xffffffffu, mn[d]);
-            const int c = __reduce_max_sync(0xffffffffu, mx[d]);
-            if (lane == 0) { red[warp * 6 + 2 * d] = a; red[warp * 6 + 2 * d + 1] = c; }
+            const int a = __reduce_min_sync(0xffffffffu, fkey(mn[d]));
+            const int c = __reduce_max_sync(0xffffffffu, fkey(mx[d]));
+            if (lane == 0) { red[(slot * NW + warp) * 8 + 2 * d] = a; red[(slot * NW + warp) * 8 + 2 * d + 1] = c; }
         }
-    }
-    plan_tile<ORDER, TX, NT>(kp, red, pb, geoms, nsub, cap, [&]() {
-#pragma unroll 1
+    };
+    auto combine = [&](int slot) -> PlaneBox {
+        PlaneBox b;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int a = kIntMax, c = kIntMin;
+            for (int w = 0; w < NW; ++w) { a = min(a, red[(slot * NW + w) * 8 + 2 * d]); c = max(c, red[(slot * NW + w) * 8 + 2 * d + 1]); }
+            const float fa = fkey_inv(a), fc = fkey_inv(c);
+            if (fa > fc) { b.mn[d] = kIntMax; b.mx[d] = kIntMin; }        // no active point
+            else { b.mn[d] = start_of<ORDER>(fa); b.mx[d] = start_of<ORDER>(fc); }
+        }
+        return b;
+    };
+    // whole tile (slot 0) + the extra maximum
+#pragma unroll
+    for (int dummy = 0; dummy < 1; ++dummy) {
+        float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
+#pragma unroll
         for (int p = 0; p < TX; ++p) {
-            int mn[3] = {kIntMax, kIntMax, kIntMax}, mx[3] = {kIntMin, kIntMin, kIntMin};
-            int i0[3];
-            const int st = support_start<T, ORDER, NT>(kp, gtile, p, col_ok && x0 + p < kp.pts_n[0], i0);
-            if (st == 1) {
+            if (col_ok && x0 + p < kp.pts_n[0]) {
+                const T *g = gtile + (p * NT + threadIdx.x) * 3;
+                const float c[3] = {(float)g[0], (float)g[1], (float)g[2]};
+                if (!masked || inbounds<float, 3>(kp, c)) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) { mn[d] = i0[d]; mx[d] = i0[d]; }
-            } else if (st == 2) {
-                mn[0] = -0x40000000; mx[0] = 0x40000000; mn[1] = mx[1] = mn[2] = mx[2] = 0;
-            }
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const int a = __reduce_min_sync(0xffffffffu, mn[d]);
-                const int c = __reduce_max_sync(0xffffffffu, mx[d]);
-                if (lane == 0) { red[(p * NW + warp) * 6 + 2 * d] = a; red[(p * NW + warp) * 6 + 2 * d + 1] = c; }
+                    for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], c[d]); mx[d] = fmaxf(mx[d], c[d]); }
+                }
             }
         }
-    });
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int a = __reduce_min_sync(0xffffffffu, fkey(mn[d]));
+            const int c = __reduce_max_sync(0xffffffffu, fkey(mx[d]));
+            if (lane == 0) { red[warp * 8 + 2 * d] = a; red[warp * 8 + 2 * d + 1] = c; }
+        }
+        const unsigned e = __reduce_max_sync(0xffffffffu, __float_as_uint(extra));
+        if (lane == 0) red[warp * 8 + kExtraSlot] = (int)e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pb[0] = combine(0);
+        geoms[0] = make_geom<ORDER>(kp, pb, 0, 1, cap);
+        *nsub = geoms[0].fits ? 1 : 0;
+        unsigned e = 0;
+        for (int w = 0; w < NW; ++w) e = max(e, (unsigned)red[w * 8 + kExtraSlot]);
+        red[kExtraSlot] = (int)e;           // slot of warp 0: read by everyone after the barrier
+    }
+    __syncthreads();
+    if (*nsub == 1) return;
+    // ---- rare: the whole-tile box does not fit -> per-plane boxes, groups of planes ----
+    const int extra_bits = red[kExtraSlot];
+    __syncthreads();
+    for (int p = 0; p < TX; ++p) reduce_planes(p, p + 1, p);
+    __syncthreads();
+    if (threadIdx.x < TX) pb[threadIdx.x] = combine(threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ns = 2;
+        for (; ns <= TX; ns *= 2) {
+            bool ok = true;
+            const int per = TX / ns;
+            for (int s = 0; s < ns; ++s) {
+                geoms[s] = make_geom<ORDER>(kp, pb, s * per, (s + 1) * per, cap);
+                ok = ok && geoms[s].fits;
+            }
+            if (ok || ns == TX) break;
+        }
+        *nsub = ns;
+        red[kExtraSlot] = extra_bits;
+    }
+    __syncthreads();
 }
 
 }  // namespace ib200

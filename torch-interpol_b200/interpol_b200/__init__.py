@@ -10,7 +10,7 @@ from .resize import *       # noqa: F401,F403
 from .restrict import *     # noqa: F401,F403
 from .autograd import (GridPull, GridPush, GridCount, GridGrad,   # noqa: F401
                        SplineCoeff, SplineCoeffND, bound_to_nitorch, inter_to_nitorch)
-from . import backend, pushpull, coeff, bounds, splines  # noqa: F401
+from . import backend, pushpull, coeff, bounds, splines, distributed  # noqa: F401
 from ._lib import launch_count, last_kernel, LIB_PATH  # noqa: F401
 
 __version__ = '0.1.0'

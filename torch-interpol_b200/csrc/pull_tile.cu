@@ -36,6 +36,7 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
     constexpr int NW = NT / 32;
     constexpr bool F32 = sizeof(T) == 4;
     constexpr bool GRAD = (OP == OP_GRAD);
+    constexpr int UI = ORDER <= 3 ? W : 1, UJ = ORDER <= 5 ? W : 1;   // keep the code of high orders compact
     static_assert(NT == TY * TZ, "one thread per (y, z) column of the tile; x-planes are looped");
     static_assert(TZ % 4 == 0, "z rows are staged 16 bytes at a time");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,11 +136,11 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
                             fast_dweights<ORDER>(cc[2] - f2, gz);
                         }
                         const float *ri = tile + ((int)f0 - g.lo[0]) * g.sxy + ((int)f1 - g.lo[1]) * g.sz + ((int)f2 - g.lo[2]);
-#pragma unroll
+#pragma unroll UI
                         for (int i = 0; i < W; ++i) {
                             const float *rj = ri;
                             float s00 = 0.f, s10 = 0.f, s01 = 0.f;
-#pragma unroll
+#pragma unroll UJ
                             for (int j = 0; j < W; ++j) {
                                 float t0 = 0.f, t1 = 0.f;
 #pragma unroll
@@ -254,6 +255,10 @@ static int dispatch_pull_tile(const KParams &kp, const void *vol, const void *gr
     case 1: return launch_pull_tile<T, 1, OP>(kp, vol, grid, out, stream);
     case 2: return launch_pull_tile<T, 2, OP>(kp, vol, grid, out, stream);
     case 3: return launch_pull_tile<T, 3, OP>(kp, vol, grid, out, stream);
+    case 4: return launch_pull_tile<T, 4, OP>(kp, vol, grid, out, stream);
+    case 5: return launch_pull_tile<T, 5, OP>(kp, vol, grid, out, stream);
+    case 6: return launch_pull_tile<T, 6, OP>(kp, vol, grid, out, stream);
+    case 7: return launch_pull_tile<T, 7, OP>(kp, vol, grid, out, stream);
     }
     return 0;
 }

@@ -40,6 +40,7 @@ push_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img
     constexpr int W = ORDER + 1;
     constexpr int NW = NT / 32;
     constexpr bool COUNT = (OP == OP_COUNT);
+    constexpr int UI = ORDER <= 3 ? W : 1, UJ = ORDER <= 5 ? W : 1;   // keep the code of high orders compact
     constexpr int QBITS = 18;              // |value| quantisation for the bound: NPT * 2^18 < 2^31
     static_assert(NT == TY * TZ, "one thread per (y, z) column of the tile; x-planes are looped");
     static_assert(NPT <= 4096, "bound histogram would overflow");
@@ -190,11 +191,11 @@ push_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img
                         fast_weights<ORDER>((float)gp[2] - (float)i0[2], wz);
                         const float v = value(p) * scale;
                         int *ri = acc + (i0[0] - g.lo[0]) * g.sxy + (i0[1] - g.lo[1]) * g.sz + (i0[2] - g.lo[2]);
-#pragma unroll
+#pragma unroll UI
                         for (int i = 0; i < W; ++i) {
                             int *rj = ri;
                             const float vi = v * wx[i];
-#pragma unroll
+#pragma unroll UJ
                             for (int j = 0; j < W; ++j) {
                                 const float vij = vi * wy[j];
 #pragma unroll
@@ -310,6 +311,10 @@ static int dispatch_push_tile(const KParams &kp, const void *img, const void *gr
     case 1: return launch_push_tile<T, 1, OP>(kp, img, grid, out, stream);
     case 2: return launch_push_tile<T, 2, OP>(kp, img, grid, out, stream);
     case 3: return launch_push_tile<T, 3, OP>(kp, img, grid, out, stream);
+    case 4: return launch_push_tile<T, 4, OP>(kp, img, grid, out, stream);
+    case 5: return launch_push_tile<T, 5, OP>(kp, img, grid, out, stream);
+    case 6: return launch_push_tile<T, 6, OP>(kp, img, grid, out, stream);
+    case 7: return launch_push_tile<T, 7, OP>(kp, img, grid, out, stream);
     }
     return 0;
 }
@@ -321,7 +326,7 @@ bool push_tiled_applicable(int op, const KParams &kp, int dtype) {
     if (dtype != IB200_F32 && dtype != IB200_F16) return false;
     if (kp.dim != 3 || !kp.pts_dense) return false;
     if (kp.order[0] != kp.order[1] || kp.order[0] != kp.order[2]) return false;
-    if (kp.order[0] < 1 || kp.order[0] > 3) return false;
+    if (kp.order[0] < 1 || kp.order[0] > 7) return false;
     if (kp.pts_total < 32768) return false;
     if (kp.pts_total * 3 > 0x7fffffffLL) return false;
     return true;

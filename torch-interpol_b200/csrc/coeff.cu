@@ -34,9 +34,12 @@ struct CoeffParams {
 // ------------------------------------------------------------------------
 // All poles of one line held in shared (or global) memory with element stride st.
 template <typename R, typename P>
-__device__ __forceinline__ void filter_line(P s, const int st, const int n, const CoeffParams &cp) {
-#define S(i) s[(i64)(i) * st]
+__device__ __forceinline__ void filter_line(P s, const int st, const int n, const CoeffParams &cp, const R gain0 = R(1)) {
+// the line holds raw samples; `gain0` (coeff.py:271 `inp *= gain`) is folded into the first pole's pass
+#define S(i) (gn * (R)s[(i64)(i) * st])
+#define SW(i) s[(i64)(i) * st]
     for (int p = 0; p < cp.npoles; ++p) {
+        const R gn = p == 0 ? gain0 : R(1);
         const R pole = (R)cp.pole[p];
         const R pp = (R)cp.pp[p];
         R init;
@@ -74,27 +77,28 @@ __device__ __forceinline__ void filter_line(P s, const int st, const int n, cons
         }
         // causal recursion, coeff.py:275-276
         R prev = init;
-        S(0) = prev;
+        SW(0) = prev;
 #pragma unroll 8
-        for (int i = 1; i < n; ++i) { prev = fma(pole, prev, (R)S(i)); S(i) = prev; }
+        for (int i = 1; i < n; ++i) { prev = fma(pole, prev, (R)S(i)); SW(i) = prev; }
         // final condition (reads the causally filtered line)
         R fin;
         if (cp.kind == 1) {                      // dct1_final, coeff.py:210-216
-            fin = (pole * (R)S(n - 2) + (R)S(n - 1)) * (R)(cp.pole[p] / (cp.pole[p] * cp.pole[p] - 1.));
+            fin = (pole * (R)SW(n - 2) + (R)SW(n - 1)) * (R)(cp.pole[p] / (cp.pole[p] * cp.pole[p] - 1.));
         } else if (cp.kind == 2) {               // dct2_final, coeff.py:220-227
-            fin = (R)S(n - 1) * (R)(cp.pole[p] / (cp.pole[p] - 1.));
+            fin = (R)SW(n - 1) * (R)(cp.pole[p] / (cp.pole[p] - 1.));
         } else {                                 // dft_final, coeff.py:183-206
             R acc = R(0), a = pp * pp;
-            for (int k = 0; k < cp.K[p] - 1; ++k) { acc = fma((R)S(k), a, acc); a *= pp; }
-            fin = fma(pole, (R)S(n - 1), acc) / (R)(cp.c1[p] - 1.);
+            for (int k = 0; k < cp.K[p] - 1; ++k) { acc = fma((R)SW(k), a, acc); a *= pp; }
+            fin = fma(pole, (R)SW(n - 1), acc) / (R)(cp.c1[p] - 1.);
         }
         // anti-causal recursion, coeff.py:280-281
         prev = fin;
-        S(n - 1) = prev;
+        SW(n - 1) = prev;
 #pragma unroll 8
-        for (int i = n - 2; i >= 0; --i) { prev = pole * (prev - (R)S(i)); S(i) = prev; }
+        for (int i = n - 2; i >= 0; --i) { prev = pole * (prev - (R)SW(i)); SW(i) = prev; }
     }
 #undef S
+#undef SW
 }
 
 // proxy so that filter_line can run directly on 16-bit global storage
@@ -112,42 +116,65 @@ struct GlobalLine {
 
 // ---------------------------------------------------------------- kernels --
 
-// inner > 1.  blockDim.x = 32 * W; every warp owns a tile of 32 lines.
+__device__ __forceinline__ void cpa16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cpa_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// inner > 1.  One warp per CTA owns a tile of 32 adjacent lines ([n][32] in shared
+// memory, lane l <-> column l: conflict free).  float32 tiles are staged with
+// 16-byte cp.async (a quarter-warp moves one 128-byte row; all n rows are in
+// flight at once, so the read runs at HBM rate instead of one row per latency)
+// and written back with 16-byte stores.
 template <typename T>
-__global__ void __launch_bounds__(128)
-coeff_strided_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data) {
+__global__ void __launch_bounds__(32)
+coeff_strided_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data, const int vec_ok) {
     typedef typename Traits<T>::Real R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane = threadIdx.x;
     const int n = (int)cp.n;
-    R *tile = reinterpret_cast<R *>(smem_raw) + (size_t)warp * n * 32;
+    R *tile = reinterpret_cast<R *>(smem_raw);
     const i64 tiles_per_outer = (cp.inner + 31) / 32;
     const i64 ntiles = cp.outer * tiles_per_outer;
     const R gain = (R)cp.gain;
-    for (i64 tidx = (i64)blockIdx.x * nwarp + warp; tidx < ntiles; tidx += (i64)gridDim.x * nwarp) {
+    for (i64 tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
         const i64 o = tidx / tiles_per_outer;
         const i64 k0 = (tidx - o * tiles_per_outer) * 32;
-        const bool active = k0 + lane < cp.inner;
-        T *g = data + o * cp.n * cp.inner + k0 + lane;
-        if (active) {
-#pragma unroll 8
-            for (int i = 0; i < n; ++i) tile[i * 32 + lane] = Traits<T>::load_rw(g + (i64)i * cp.inner) * gain;
-            filter_line<R>(tile + lane, 32, n, cp);
-#pragma unroll 8
+        const bool full = k0 + 32 <= cp.inner;
+        T *g0 = data + o * cp.n * cp.inner + k0;
+        if (sizeof(T) == 4 && sizeof(R) == 4 && vec_ok && full) {
+            const int rsub = lane >> 3, ch = (lane & 7) * 4;
+            for (int i = rsub; i < n; i += 4) cpa16(tile + i * 32 + ch, g0 + (i64)i * cp.inner + ch);
+            cpa_wait_all();
+            __syncwarp();
+            filter_line<R>(tile + lane, 32, n, cp, gain);
+            __syncwarp();
+            for (int i = rsub; i < n; i += 4)
+                *reinterpret_cast<float4 *>(g0 + (i64)i * cp.inner + ch) = *reinterpret_cast<const float4 *>(tile + i * 32 + ch);
+        } else if (k0 + lane < cp.inner) {
+            T *g = g0 + lane;
+#pragma unroll 16
+            for (int i = 0; i < n; ++i) tile[i * 32 + lane] = Traits<T>::load_rw(g + (i64)i * cp.inner);
+            filter_line<R>(tile + lane, 32, n, cp, gain);
+#pragma unroll 16
             for (int i = 0; i < n; ++i) Traits<T>::store(g + (i64)i * cp.inner, tile[i * 32 + lane]);
         }
         __syncwarp();
     }
 }
 
-// inner == 1.  A CTA stages L = blockDim.x whole lines (contiguous in memory).
+// inner == 1.  A CTA of 256 threads stages L whole lines (a contiguous block of L*n
+// elements) with an odd row stride, L threads filter one line each, everybody
+// writes back.  Loads are issued 8 deep per thread to cover the HBM latency.
 template <typename T>
 __global__ void __launch_bounds__(256)
-coeff_contig_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data, int row_stride) {
+coeff_contig_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data, const int row_stride, const int L) {
     typedef typename Traits<T>::Real R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tile = reinterpret_cast<R *>(smem_raw);
-    const int n = (int)cp.n, L = blockDim.x;
+    const int n = (int)cp.n, NT = blockDim.x;
     const i64 nblk = (cp.outer + L - 1) / L;
     const R gain = (R)cp.gain;
     for (i64 blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
@@ -155,16 +182,33 @@ coeff_contig_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data
         const int nl = (int)((cp.outer - l0) < L ? (cp.outer - l0) : L);
         T *g = data + l0 * n;
         const int count = nl * n;
-        for (int e = threadIdx.x; e < count; e += L) {
-            const int l = e / n, i = e - l * n;
-            tile[l * row_stride + i] = Traits<T>::load_rw(g + e) * gain;
+        // (l, i) of element e = threadIdx.x + k * NT is tracked incrementally: no division
+        const int dl = NT / n, di = NT - dl * n;          // NT = dl * n + di
+        {
+            int l = threadIdx.x / n, i = threadIdx.x - l * n;
+            for (int e0 = threadIdx.x; e0 < count; e0 += NT * 8) {
+                R v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int e = e0 + u * NT; v[u] = e < count ? (R)Traits<T>::load_rw(g + e) : R(0); }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (e0 + u * NT < count) tile[l * row_stride + i] = v[u];
+                    l += dl; i += di;
+                    if (i >= n) { i -= n; ++l; }
+                }
+            }
         }
         __syncthreads();
-        if ((int)threadIdx.x < nl) filter_line<R>(tile + threadIdx.x * row_stride, 1, n, cp);
+        if ((int)threadIdx.x < nl) filter_line<R>(tile + threadIdx.x * row_stride, 1, n, cp, gain);
         __syncthreads();
-        for (int e = threadIdx.x; e < count; e += L) {
-            const int l = e / n, i = e - l * n;
-            Traits<T>::store(g + e, tile[l * row_stride + i]);
+        {
+            int l = threadIdx.x / n, i = threadIdx.x - l * n;
+#pragma unroll 4
+            for (int e = threadIdx.x; e < count; e += NT) {
+                Traits<T>::store(g + e, tile[l * row_stride + i]);
+                l += dl; i += di;
+                if (i >= n) { i -= n; ++l; }
+            }
         }
         __syncthreads();
     }
@@ -180,9 +224,8 @@ coeff_global_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data
     for (i64 l = (i64)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (i64)gridDim.x * blockDim.x) {
         const i64 o = l / cp.inner, k = l - o * cp.inner;
         T *g = data + o * cp.n * cp.inner + k;
-        for (i64 i = 0; i < cp.n; ++i) Traits<T>::store(g + i * cp.inner, Traits<T>::load_rw(g + i * cp.inner) * gain);
-        if (sizeof(T) == sizeof(R)) filter_line<R>(reinterpret_cast<R *>(g), (int)cp.inner, (int)cp.n, cp);
-        else filter_line<R>(GlobalLine<T>{g}, (int)cp.inner, (int)cp.n, cp);
+        if (sizeof(T) == sizeof(R)) filter_line<R>(reinterpret_cast<R *>(g), (int)cp.inner, (int)cp.n, cp, gain);
+        else filter_line<R>(GlobalLine<T>{g}, (int)cp.inner, (int)cp.n, cp, gain);
     }
 }
 // ---------------------------------------------------------------- launch --
@@ -219,31 +262,30 @@ static int launch_typed(const CoeffParams &cp, void *data, cudaStream_t stream) 
     const size_t kSmemCap = 200 * 1024;
     T *d = (T *)data;
     if (cp.inner > 1) {
-        const size_t per_warp = (size_t)cp.n * 32 * sizeof(R);
-        if (per_warp <= kSmemCap) {
-            int warps = 1;   // one warp per CTA keeps the smem granularity fine
+        const size_t smem = (size_t)cp.n * 32 * sizeof(R);
+        if (smem <= kSmemCap) {
             const i64 ntiles = cp.outer * ((cp.inner + 31) / 32);
-            i64 blocks = (ntiles + warps - 1) / warps;
+            i64 blocks = ntiles;
             const i64 cap = (i64)kNumSMs * 32;
             if (blocks > cap) blocks = cap;
-            const size_t smem = per_warp * warps;
+            const int vec_ok = ((uintptr_t)data % 16 == 0) && (cp.inner % 4 == 0);
             IB200_CUDA_CHECK(cudaFuncSetAttribute(coeff_strided_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            coeff_strided_kernel<T><<<(unsigned)blocks, 32 * warps, smem, stream>>>(cp, d);
+            coeff_strided_kernel<T><<<(unsigned)blocks, 32, smem, stream>>>(cp, d, vec_ok);
             note_launch("coeff_strided");
             IB200_CUDA_CHECK(cudaGetLastError());
             return IB200_OK;
         }
     } else {
         int row_stride = (int)cp.n | 1;   // odd stride: lane l, element i -> distinct banks
-        int L = 256;
-        while (L > 32 && (size_t)L * row_stride * sizeof(R) > 64 * 1024) L >>= 1;
+        int L = 64;
+        while (L > 8 && (size_t)L * row_stride * sizeof(R) > 72 * 1024) L >>= 1;
         const size_t smem = (size_t)L * row_stride * sizeof(R);
         if (smem <= kSmemCap) {
             i64 blocks = (cp.outer + L - 1) / L;
             const i64 cap = (i64)kNumSMs * 16;
             if (blocks > cap) blocks = cap;
             IB200_CUDA_CHECK(cudaFuncSetAttribute(coeff_contig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            coeff_contig_kernel<T><<<(unsigned)blocks, L, smem, stream>>>(cp, d, row_stride);
+            coeff_contig_kernel<T><<<(unsigned)blocks, 256, smem, stream>>>(cp, d, row_stride, L);
             note_launch("coeff_contig");
             IB200_CUDA_CHECK(cudaGetLastError());
             return IB200_OK;

@@ -77,7 +77,10 @@ enum {
     IB200_FLAG_NO_TILES = 1u << 0,
     /* reproduce the reference's sign error for d/dx of the order-1 spline on an
      * axis of a mixed-order call (splines.py:96-97); default is the true derivative */
-    IB200_FLAG_REF_LINEAR_GRAD_SIGN = 1u << 1
+    IB200_FLAG_REF_LINEAR_GRAD_SIGN = 1u << 1,
+    /* never take the persistent warp-specialised kernels (fall back to the one-tile-per-CTA
+     * tiled kernels; A/B testing, profiling) */
+    IB200_FLAG_NO_PIPE = 1u << 2
 };
 
 /*

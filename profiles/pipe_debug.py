@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Phase timers of the pull pipe kernel (CTA 0: producer warp and consumer warp 0), in SM clock ticks.
+    python profiles/pipe_debug.py [--order N] [--channels C] [--bound B]"""
+import ctypes, os, sys
+os.environ['IB200_PIPE_DEBUG'] = '1'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'torch-interpol_b200')); sys.path.insert(0, ROOT)
+import torch
+from bench import make_workload
+import interpol_b200 as ib
+from interpol_b200 import pushpull as pp, _lib
+
+
+def arg(name, default):
+    return int(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+
+order, C, bound = arg('--order', 3), arg('--channels', 1), arg('--bound', 3)
+vol, grid = make_workload(256, 'cuda')
+vol = vol.expand(1, C, 256, 256, 256).contiguous()
+for _ in range(3):
+    pp.grid_pull(vol, grid, [bound], [order], 1)
+torch.cuda.synchronize()
+a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+a.record(); pp.grid_pull(vol, grid, [bound], [order], 1); b.record(); torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 16)()
+_lib.lib().ib200_debug_pipe_counters(buf)
+names = ['P wait kfull', 'P plan', 'P request grid', 'P wait bempty', 'P issue box', 'C wait gfull', 'C wait bfull',
+         'C geom+fixup', 'C rows (taps)', 'C merge+release', 'C items', 'C whole loop']
+items = max(buf[10], 1)
+print('order', order, 'C', C, 'bound', bound, 'kernel %.1f us' % (a.elapsed_time(b) * 1e3), ib.last_kernel(), 'items', items)
+for i, nm in enumerate(names):
+    print('%-16s total %10d ticks   per item %8.0f' % (nm, buf[i], buf[i] / items))

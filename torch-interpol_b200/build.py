@@ -43,7 +43,7 @@ DTYPES = {
 def units():
     """(source, object name, extra defines)"""
     out = [('abi.cu', 'abi.o', []), ('coeff.cu', 'coeff.o', [])]
-    for extra in ('pull_tile.cu', 'push_tile.cu', 'tiles_stub.cu'):
+    for extra in ('pull_tile.cu', 'push_tile.cu', 'pull_pipe.cu', 'push_pipe.cu'):
         if os.path.exists(os.path.join(CSRC, extra)):
             out.append((extra, extra.replace('.cu', '.o'), []))
     for name, (ctype, acc, orders) in DTYPES.items():
@@ -55,13 +55,34 @@ def units():
     return out
 
 
-def newest_header():
-    t = 0.0
-    for f in os.listdir(CSRC):
-        if f.endswith(('.cuh', '.h')):
-            t = max(t, os.path.getmtime(os.path.join(CSRC, f)))
-    t = max(t, os.path.getmtime(os.path.join(HERE, '..', 'include', 'interpol_b200.h')))
-    t = max(t, os.path.getmtime(os.path.abspath(__file__)))
+_INC_CACHE = {}
+
+
+def header_deps(path):
+    """headers (transitively) included with #include "..." by `path`"""
+    path = os.path.normpath(path)
+    if path in _INC_CACHE:
+        return _INC_CACHE[path]
+    deps = set()
+    _INC_CACHE[path] = deps
+    try:
+        with open(path) as f:
+            for line in f:
+                line = line.strip()
+                if line.startswith('#include "'):
+                    h = os.path.normpath(os.path.join(os.path.dirname(path), line.split('"')[1]))
+                    if os.path.exists(h):
+                        deps.add(h)
+                        deps |= header_deps(h)
+    except OSError:
+        pass
+    return deps
+
+
+def newest_dep(src):
+    t = os.path.getmtime(os.path.abspath(__file__))
+    for h in header_deps(os.path.join(CSRC, src)):
+        t = max(t, os.path.getmtime(h))
     return t
 
 
@@ -78,13 +99,12 @@ def compile_one(src, obj, defs, verbose):
 def build(force=False, jobs=None, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(OUT_DIR, exist_ok=True)
-    hdr = newest_header()
     todo, objs = [], []
     for src, obj, defs in units():
         objs.append(os.path.join(OBJ, obj))
         o = os.path.join(OBJ, obj)
         stale = force or not os.path.exists(o) or \
-            os.path.getmtime(o) < max(hdr, os.path.getmtime(os.path.join(CSRC, src)))
+            os.path.getmtime(o) < max(newest_dep(src), os.path.getmtime(os.path.join(CSRC, src)))
         if stale:
             todo.append((src, obj, defs))
     if todo:

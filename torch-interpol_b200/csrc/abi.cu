@@ -136,6 +136,8 @@ static int run_gather(int op, const ib200_problem *p, const void *vol, const voi
     if (!guard.ok) return IB200_ERR_CUDA - (int)cudaErrorInvalidDevice;
     cudaStream_t s = (cudaStream_t)stream;
     if ((op == OP_PULL || op == OP_GRAD) && !(p->flags & IB200_FLAG_NO_TILES)) {
+        st = try_pull_pipe(op, kp, p->dtype, vol, grid, out, s);
+        if (st != 0) return st < 0 ? st : IB200_OK;
         st = try_pull_tiled(op, kp, p->dtype, vol, grid, out, s);
         if (st != 0) return st < 0 ? st : IB200_OK;
     }

@@ -107,6 +107,8 @@ int launch_coeff(void *data, int dtype, i64 outer, i64 n, i64 inner, int bound, 
 // tiled fast paths: return 1 when they handled the call, 0 when not applicable, <0 on error
 int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out,
                    cudaStream_t stream);
+int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out,
+                  cudaStream_t stream);
 bool push_tiled_applicable(int op, const KParams &kp, int dtype);
 int try_push_tiled(int op, const KParams &kp, int dtype, const void *img, const void *grid,
                    void *acc, cudaStream_t stream);   // acc: zero-filled float32 accumulation volume

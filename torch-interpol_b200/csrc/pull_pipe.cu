@@ -1,0 +1,447 @@
+// Persistent warp-specialised pull / grad (3-D, isotropic compile-time order,
+// float32 storage): the tiled gather of pull_tile.cu restructured so that the tap
+// loop never waits for memory.
+//
+//   grid = one CTA per SM, each looping over tiles of 8 x 8 x 32 output voxels.
+//   warp 0 (producer)
+//     - streams the grid coordinates of tiles n+1, n+2 into a 3-deep ring, one TMA
+//       tile copy (cp.async.bulk.tensor, box 8 x 8 x 96 floats) per tile;
+//     - reduces the bounding box of all spline supports of tile n (REDUX);
+//     - issues one TMA tile copy per x-plane of the box of the input volume (box
+//       16 rows x 64 words) into a 2-deep ring of boxes; the TMA unit zero-fills
+//       whatever lies outside the volume, which IS the `zero` boundary condition;
+//       for the other bounds a fix-up pass rewrites the out-of-volume elements.
+//   warps 1.. (consumers)
+//     - wait on the box's mbarrier, (rarely) fix up folded elements, then evaluate
+//       (ORDER+1)^3 LDS taps per voxel and store the result; rows are 64 words so
+//       that the bank of a tap depends on z only.
+//   Boxes that do not fit (incoherent deformation) are gathered from global
+//   memory by the consumers with identical arithmetic.
+//
+// Replaces interpol/nd.py:81-143 / :217-288 (and iso1.py) for the shapes that
+// matter for throughput; pull_tile.cu / gather.cu cover the rest.
+#include <cstdio>
+#include <cstdlib>
+#include "pipe_common.cuh"
+
+namespace ib200 {
+
+// Phase timers (clock64 ticks, accumulated in registers by the producer warp and consumer warp 0 of
+// CTA 0, written once at kernel exit) -- filled only when IB200_PIPE_DEBUG is set in the environment.
+__device__ long long g_pipe_dbg[16];
+#define TICK(var) const long long var = dbg ? clock64() : 0
+#define TOCK(acc, var) do { if (dbg) acc += clock64() - (var); } while (0)
+
+constexpr int kNG = 4;     // ring of grid-coordinate tiles
+constexpr int kNB = 2;     // ring of boxes
+
+template <int ORDER, int OP, int W>
+__device__ __noinline__ float3 pull_point_global(const KParams &kp, const float *src, float c0, float c1, float c2) {
+    constexpr bool GRAD = (OP == OP_GRAD);
+    const float cc[3] = {c0, c1, c2};
+    float acc = 0.f, ag[3] = {0.f, 0.f, 0.f};
+    if (inbounds<float, 3>(kp, cc)) {
+        Axis<float, W> ax[3];
+        bool ok = setup_axis<float, ORDER, GRAD ? 1 : 0, W>(ax[0], cc[0], ORDER, kp.bound[0], kp.vol_n[0], (int)kp.vol_s[0], kp);
+        ok = setup_axis<float, ORDER, GRAD ? 1 : 0, W>(ax[1], cc[1], ORDER, kp.bound[1], kp.vol_n[1], (int)kp.vol_s[1], kp) && ok;
+        ok = setup_axis<float, ORDER, GRAD ? 1 : 0, W>(ax[2], cc[2], ORDER, kp.bound[2], kp.vol_n[2], (int)kp.vol_s[2], kp) && ok;
+        if (ok) {
+#pragma unroll 1
+            for (int i = 0; i < W; ++i) {
+                float s00 = 0.f, s10 = 0.f, s01 = 0.f;
+#pragma unroll 1
+                for (int j = 0; j < W; ++j) {
+                    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        const float v = __ldg(src + ax[0].off[i] + ax[1].off[j] + ax[2].off[k]);
+                        t0 = fmaf(ax[2].w[k], v, t0);
+                        if (GRAD) t1 = fmaf(ax[2].g[k], v, t1);
+                    }
+                    s00 = fmaf(ax[1].w[j], t0, s00);
+                    if (GRAD) { s10 = fmaf(ax[1].g[j], t0, s10); s01 = fmaf(ax[1].w[j], t1, s01); }
+                }
+                if (!GRAD) acc = fmaf(ax[0].w[i], s00, acc);
+                else { ag[0] = fmaf(ax[0].g[i], s00, ag[0]); ag[1] = fmaf(ax[0].w[i], s10, ag[1]); ag[2] = fmaf(ax[0].w[i], s01, ag[2]); }
+            }
+        }
+    }
+    return GRAD ? make_float3(ag[0], ag[1], ag[2]) : make_float3(acc, 0.f, 0.f);
+}
+
+template <int ORDER, int OP, int NCW>
+__global__ void __launch_bounds__(32 * (NCW + 1), 1)
+pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ CUtensorMap tm_vol,
+                   const __grid_constant__ CUtensorMap tm_grid, const float *__restrict__ vol,
+                   float *__restrict__ out, const int ntiles, const int cmul, const int bmul, const int gbmul,
+                   const unsigned inv_ntz, const unsigned inv_nty, const unsigned inv_ntx, long long *dbg) {
+    constexpr int TX = 8, TY = 8, TZ = 32;
+    constexpr int NPT = TX * TY * TZ;
+    constexpr int NROWS = TX * TY;
+    constexpr int W = ORDER + 1;
+    constexpr bool GRAD = (OP == OP_GRAD);
+    constexpr int NCT = NCW * 32;                  // consumer threads
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *box = reinterpret_cast<float *>(smem_raw);                                   // [kNB][kBoxWords]
+    float *gtile = box + (size_t)kNB * kBoxWords;                                       // [kNG][NPT * 3]
+    PipeGeom *geoms = reinterpret_cast<PipeGeom *>(gtile + (size_t)kNG * NPT * 3);      // [kNB]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(geoms + kNB);
+    unsigned long long *gfull = bars, *gempty = bars + kNG, *bfull = bars + 2 * kNG, *bempty = bars + 2 * kNG + kNB;
+    unsigned long long *kfull = bars + 2 * kNG + 2 * kNB;                               // [2] box of a tile reduced
+    int *rowctr = reinterpret_cast<int *>(bars + 2 * kNG + 2 * kNB + 2);                // [kNB] next unclaimed z-row
+    int *keys_base = rowctr + kNB;                                                      // [2][6] boxes of tiles j, j+1 (+2 pad each)
+    int *qkeys = keys_base + 16;                                                        // [24] quarter boxes (rare)
+    PipeGeom *planned = reinterpret_cast<PipeGeom *>(qkeys + 24);                       // [4] parts of the planned tile
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kNG; ++i) { mbar_init(gfull + i, 1); mbar_init(gempty + i, NCW); }
+        for (int i = 0; i < kNB; ++i) { mbar_init(bfull + i, 1); mbar_init(bempty + i, NCW); }
+        mbar_init(kfull, NCW); mbar_init(kfull + 1, NCW);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        tma_prefetch_desc(&tm_vol);
+        tma_prefetch_desc(&tm_grid);
+    }
+    if (threadIdx.x < 16) keys_base[threadIdx.x] = pipe_key_init(threadIdx.x);
+    __syncthreads();
+
+    const int ntx = (kp.pts_n[0] + TX - 1) / TX, nty = (kp.pts_n[1] + TY - 1) / TY, ntz = (kp.pts_n[2] + TZ - 1) / TZ;
+    const int C = (int)kp.channels;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... (neighbouring CTAs work on neighbouring
+    // tiles at the same time, so halos are shared through L2)
+    const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto decode = [&](int q, int &b, int &x0, int &y0, int &z0) {
+        const int t = (int)blockIdx.x + q * (int)gridDim.x;
+        const int t1 = fast_div(t, inv_ntz), t2 = fast_div(t1, inv_nty), t3 = fast_div(t2, inv_ntx);
+        b = t3; x0 = (t2 - t3 * ntx) * TX; y0 = (t1 - t2 * nty) * TY; z0 = (t - t1 * ntz) * TZ;
+    };
+
+    // Schedule.  The box of tile j is reduced by the consumers while they process tile j-2 (its
+    // coordinates arrive one tile earlier still), turned into a plan + TMA requests by the producer
+    // when tile j-2 releases its buffer, and lands while the consumers process tile j-1: nothing on
+    // the consumers' path ever waits for memory or for the (slow, single-warp) producer.
+    if (warp == NCW) {
+        // ================================ producer ================================
+        auto request_grid = [&](int q) {
+            int b, x0, y0, z0;
+            decode(q, b, x0, y0, z0);
+            const int s = q % kNG, u = q / kNG;
+            if (u > 0) mbar_wait(gempty + s, (u - 1) & 1);
+            if (lane == 0) {
+                mbar_expect_tx(gfull + s, NPT * 3 * 4);
+                tma_load_4d(gtile + (size_t)s * NPT * 3, &tm_grid, z0 * 3, y0, x0, b * gbmul, gfull + s);
+                mbar_arrive(gfull + s);
+            }
+        };
+        if (my_tiles > 0) request_grid(0);
+        if (my_tiles > 1) request_grid(1);
+        int n = 0;                                   // box sequence number
+        long long a_kfull = 0, a_plan = 0, a_grid = 0, a_bempty = 0, a_issue = 0;
+        for (int j = 0; j < my_tiles; ++j) {
+            int b, x0, y0, z0;
+            decode(j, b, x0, y0, z0);
+            // ---- plan: whole tile, z halves or z quarters ----
+            TICK(t_k);
+            mbar_wait(kfull + (j & 1), (j >> 1) & 1);
+            TOCK(a_kfull, t_k);
+            TICK(t_p);
+            int nparts = 1;
+            {
+                PipeGeom g0 = pipe_geom<ORDER>(kp, keys_base + (j & 1) * 8, 0, 1);
+                g0.zlo = 0; g0.zhi = TZ; g0.last = 1;
+                if (g0.mode != PIPE_GLOBAL) {
+                    if (lane == 0) planned[0] = g0;
+                } else {
+                    const int nxv = min(TX, kp.pts_n[0] - x0), nyv = min(TY, kp.pts_n[1] - y0), nzv = min(TZ, kp.pts_n[2] - z0);
+                    pipe_quarter_boxes<TX, TY, TZ>(kp, gtile + (size_t)(j % kNG) * NPT * 3, nxv, nyv, nzv, qkeys);
+                    g0 = pipe_geom<ORDER>(kp, qkeys, 0, 2);
+                    const PipeGeom g1 = pipe_geom<ORDER>(kp, qkeys, 2, 4);
+                    if (g0.mode != PIPE_GLOBAL && g1.mode != PIPE_GLOBAL) {
+                        nparts = 2;
+                        if (lane == 0) { planned[0] = g0; planned[1] = g1; }
+                    } else {
+                        nparts = 4;
+                        for (int p = 0; p < 4; ++p) {
+                            const PipeGeom gq = pipe_geom<ORDER>(kp, qkeys, p, p + 1);
+                            if (lane == 0) planned[p] = gq;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane < 6) keys_base[(j & 1) * 8 + lane] = pipe_key_init(lane);      // ready for tile j + 2
+                __syncwarp();
+            }
+            // coordinates of tile j + 2 (their buffer was released with tile j - 2).  Must precede the boxes:
+            // the consumers wait for them before they touch (and can release) the first part of tile j.
+            TOCK(a_plan, t_p);
+            TICK(t_g);
+            if (j + 2 < my_tiles) request_grid(j + 2);
+            TOCK(a_grid, t_g);
+            // ---- one box per (channel, part) ----
+            for (int c = 0; c < C; ++c) {
+                for (int part = 0; part < nparts; ++part, ++n) {
+                    const PipeGeom g = planned[part];
+                    const int s = n % kNB, u = n / kNB;
+                    TICK(t_b);
+                    if (u > 0) mbar_wait(bempty + s, (u - 1) & 1);
+                    TOCK(a_bempty, t_b);
+                    TICK(t_i);
+                    if (lane == 0) {
+                        geoms[s] = g;
+                        rowctr[s] = 0;
+                        if (g.mode == PIPE_PLAIN || g.mode == PIPE_FOLD) mbar_expect_tx(bfull + s, (unsigned)g.ext[0] * kBoxPlane * 4u);
+                    }
+                    __syncwarp();
+                    if ((g.mode == PIPE_PLAIN || g.mode == PIPE_FOLD) && lane < g.ext[0])
+                        tma_load_5d(box + (size_t)s * kBoxWords + lane * kBoxPlane, &tm_vol, g.lo[2], g.lo[1], g.lo[0] + lane,
+                                    c * cmul, b * bmul, bfull + s);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bfull + s);
+                    TOCK(a_issue, t_i);
+                }
+            }
+        }
+        if (dbg && blockIdx.x == 0 && lane == 0) { dbg[0] = a_kfull; dbg[1] = a_plan; dbg[2] = a_grid; dbg[3] = a_bempty; dbg[4] = a_issue; }
+    } else {
+        // ================================ consumers ===============================
+        const int ct = threadIdx.x;
+        const bool masked = kp.extrapolate != 1;
+        for (int q = 0; q < 2 && q < my_tiles; ++q) {      // boxes of the first two tiles, cooperatively
+            int b, x0, y0, z0;
+            decode(q, b, x0, y0, z0);
+            mbar_wait(gfull + q % kNG, (q / kNG) & 1);
+            pipe_tile_box<TX, TY, TZ, NCW>(kp, gtile + (size_t)(q % kNG) * NPT * 3, min(TX, kp.pts_n[0] - x0), min(TY, kp.pts_n[1] - y0),
+                                           min(TZ, kp.pts_n[2] - z0), keys_base + (q & 1) * 8, warp);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(kfull + (q & 1));
+        }
+        int n = 0;
+        long long a_gfull = 0, a_bfull = 0, a_fix = 0, a_rows = 0, a_rel = 0, a_items = 0;
+        TICK(t_all);
+        for (int q = 0; q < my_tiles; ++q) {
+            int b, x0, y0, z0;
+            decode(q, b, x0, y0, z0);
+            const int nxv = min(TX, kp.pts_n[0] - x0), nyv = min(TY, kp.pts_n[1] - y0), nzv = min(TZ, kp.pts_n[2] - z0);
+            const float *gt = gtile + (size_t)(q % kNG) * NPT * 3;
+            // while the rows of tile q are evaluated, the box of tile q + 2 is reduced on the side
+            bool look = q + 2 < my_tiles;
+            int nxv2 = 0, nyv2 = 0, nzv2 = 0;
+            const float *gt2 = gtile + (size_t)((q + 2) % kNG) * NPT * 3 + lane * 3;
+            float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
+            if (look) {
+                int b2, x2, y2, z2;
+                decode(q + 2, b2, x2, y2, z2);
+                nxv2 = min(TX, kp.pts_n[0] - x2); nyv2 = min(TY, kp.pts_n[1] - y2); nzv2 = min(TZ, kp.pts_n[2] - z2);
+                TICK(t_g);
+                mbar_wait(gfull + (q + 2) % kNG, ((q + 2) / kNG) & 1);
+                TOCK(a_gfull, t_g);
+            }
+            for (int c = 0; c < C; ++c) {
+                const float *src = vol + (i64)b * kp.vol_sb + (i64)c * kp.vol_sc;
+                float *dst = out + ((i64)b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1);
+                bool last;
+                do {
+                    const int s = n % kNB;
+                    TICK(t_b);
+                    mbar_wait(bfull + s, (n / kNB) & 1);
+                    TOCK(a_bfull, t_b);
+                    TICK(t_f);
+                    const PipeGeom g = geoms[s];
+                    last = g.last != 0;
+                    float *bx = box + (size_t)s * kBoxWords;
+                    if (g.mode == PIPE_FOLD) {
+                        pipe_fixup(kp, g, bx, src, ct, NCT);
+                        named_bar_sync(1, NCT);
+                    }
+                    TOCK(a_fix, t_f);
+                    TICK(t_r);
+                    // ---- taps: z-rows of the tile are claimed dynamically (a slow warp never holds the box) ----
+                    const bool lane_ok = lane < nzv && lane >= g.zlo && lane < g.zhi;
+                    int r = 0;
+                    if (lane == 0) r = atomicAdd(rowctr + s, 1);
+                    r = __shfl_sync(0xffffffffu, r, 0);
+                    while (r < NROWS) {
+                        int rn = 0;
+                        if (lane == 0) rn = atomicAdd(rowctr + s, 1);      // claimed early: its latency hides behind the taps
+                        const int p = r / TY, ly = r - p * TY;
+                        if (look) {
+                            const float c2[3] = {gt2[r * (TZ * 3)], gt2[r * (TZ * 3) + 1], gt2[r * (TZ * 3) + 2]};
+                            const bool use = p < nxv2 && ly < nyv2 && lane < nzv2 && (!masked || inbounds<float, 3>(kp, c2));
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                mn[d] = fminf(mn[d], use ? c2[d] : 3e38f);
+                                mx[d] = fmaxf(mx[d], use ? c2[d] : -3e38f);
+                            }
+                        }
+                        if (p < nxv && ly < nyv && lane_ok) {
+                            const float *gp = gt + (r * TZ + lane) * 3;
+                            const float cc[3] = {gp[0], gp[1], gp[2]};
+                            float res[3] = {0.f, 0.f, 0.f};
+                            if (g.mode == PIPE_GLOBAL) {
+                                const float3 r3 = pull_point_global<ORDER, OP, W>(kp, src, cc[0], cc[1], cc[2]);
+                                res[0] = r3.x; res[1] = r3.y; res[2] = r3.z;
+                            } else if (g.mode != PIPE_EMPTY) {
+                                const float f0 = floorf(cc[0] - 0.5f * (ORDER - 1)), f1 = floorf(cc[1] - 0.5f * (ORDER - 1)),
+                                            f2 = floorf(cc[2] - 0.5f * (ORDER - 1));
+                                const bool actp = inbounds<float, 3>(kp, cc) && fabsf(f0) < 4e18f && fabsf(f1) < 4e18f && fabsf(f2) < 4e18f;
+                                if (actp) {
+                                    float wx[W], wy[W], wz[W], gx[W], gy[W], gz[W];
+                                    fast_weights<ORDER>(cc[0] - f0, wx);
+                                    fast_weights<ORDER>(cc[1] - f1, wy);
+                                    fast_weights<ORDER>(cc[2] - f2, wz);
+                                    if (GRAD) {
+                                        fast_dweights<ORDER>(cc[0] - f0, gx);
+                                        fast_dweights<ORDER>(cc[1] - f1, gy);
+                                        fast_dweights<ORDER>(cc[2] - f2, gz);
+                                    }
+                                    const float *ri = bx + ((int)f0 - g.lo[0]) * kBoxPlane + ((int)f1 - g.lo[1]) * kBoxZ + ((int)f2 - g.lo[2]);
+                                    float acc = 0.f, ax_ = 0.f, ay_ = 0.f, az_ = 0.f;
+#pragma unroll
+                                    for (int i = 0; i < W; ++i) {
+                                        float s00 = 0.f, s10 = 0.f, s01 = 0.f;
+#pragma unroll
+                                        for (int jj = 0; jj < W; ++jj) {
+                                            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                                            for (int k = 0; k < W; ++k) {
+                                                const float v = ri[i * kBoxPlane + jj * kBoxZ + k];
+                                                t0 = fmaf(wz[k], v, t0);
+                                                if (GRAD) t1 = fmaf(gz[k], v, t1);
+                                            }
+                                            s00 = fmaf(wy[jj], t0, s00);
+                                            if (GRAD) { s10 = fmaf(gy[jj], t0, s10); s01 = fmaf(wy[jj], t1, s01); }
+                                        }
+                                        if (!GRAD) acc = fmaf(wx[i], s00, acc);
+                                        else { ax_ = fmaf(gx[i], s00, ax_); ay_ = fmaf(wx[i], s10, ay_); az_ = fmaf(wx[i], s01, az_); }
+                                    }
+                                    if (!GRAD) res[0] = acc;
+                                    else { res[0] = ax_; res[1] = ay_; res[2] = az_; }
+                                }
+                            }
+                            const int o = ((x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lane);
+                            if (!GRAD) dst[o] = res[0];
+                            else { dst[o * 3] = res[0]; dst[o * 3 + 1] = res[1]; dst[o * 3 + 2] = res[2]; }
+                        }
+                        r = __shfl_sync(0xffffffffu, rn, 0);
+                    }
+                    TOCK(a_rows, t_r);
+                    TICK(t_e);
+                    if (look) {
+                        // every row of the tile has been claimed exactly once: the box of tile q + 2 is complete
+                        pipe_merge_box(mn, mx, keys_base + (q & 1) * 8);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(kfull + (q & 1));
+                        look = false;
+                    }
+                    // ---- release the box (and, after the last part of the last channel, the coordinates) ----
+                    if (g.mode == PIPE_FOLD) fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bempty + s);
+                        if (last && c == C - 1) mbar_arrive(gempty + q % kNG);
+                    }
+                    ++n;
+                    TOCK(a_rel, t_e);
+                    a_items += 1;
+                } while (!last);
+            }
+        }
+        if (dbg && blockIdx.x == 0 && warp == 0 && lane == 0) {
+            dbg[5] = a_gfull; dbg[6] = a_bfull; dbg[7] = a_fix; dbg[8] = a_rows; dbg[9] = a_rel; dbg[10] = a_items;
+            dbg[11] = clock64() - t_all;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launch --
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else n = kNumSMs;
+    }
+    return n;
+}
+
+template <int ORDER, int OP, int NCW>
+static int launch_pull_pipe(const KParams &kp, const float *vol, const float *grid, float *out, cudaStream_t stream) {
+    constexpr int NPT = 8 * 8 * 32;
+    const size_t smem_total = (size_t)kNB * kBoxWords * 4 + (size_t)kNG * NPT * 3 * 4 + kNB * sizeof(PipeGeom) +
+                              (2 * kNG + 2 * kNB + 2) * sizeof(unsigned long long) + (kNB + 40) * sizeof(int) + 4 * sizeof(PipeGeom) + 64;
+    const i64 ntiles = kp.batch * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
+    if (ntiles == 0) return 1;
+    if (ntiles * kp.channels > 0x3fffffffLL) return 0;
+    // tensor maps: volume (z, y, x, c, b), box {64, 16, 1, 1, 1}; grid (z*3, y, x, b), box {96, 8, 8, 1}
+    CUtensorMap tm_vol, tm_grid;
+    const long long vbytes = (((long long)kp.vol_n[0] * kp.vol_s[0]) + 3) & ~3LL;
+    const int cmul = (kp.vol_sc != 0 && kp.channels > 1) ? 1 : 0, bmul = (kp.vol_sb != 0 && kp.batch > 1) ? 1 : 0;
+    const int gbmul = (kp.grid_sb != 0 && kp.batch > 1) ? 1 : 0;
+    {
+        const long long dim[5] = {kp.vol_n[2], kp.vol_n[1], kp.vol_n[0], cmul ? kp.channels : 1, bmul ? kp.batch : 1};
+        const long long str[5] = {1, kp.vol_n[1] > 1 ? kp.vol_s[1] : kp.vol_n[2], kp.vol_n[0] > 1 ? kp.vol_s[0] : vbytes,
+                                  cmul ? kp.vol_sc : vbytes, bmul ? kp.vol_sb : vbytes};
+        const int box[5] = {kBoxZ, kBoxY, 1, 1, 1};
+        if (!make_tensor_map(&tm_vol, vol, 5, dim, str, box)) return 0;
+    }
+    {
+        const long long row = (long long)kp.pts_n[2] * 3;
+        const long long dim[4] = {row, kp.pts_n[1], kp.pts_n[0], gbmul ? kp.batch : 1};
+        const long long str[4] = {1, row, row * kp.pts_n[1], gbmul ? kp.grid_sb : row * kp.pts_n[1] * kp.pts_n[0]};
+        const int box[4] = {96, 8, 8, 1};
+        if (!make_tensor_map(&tm_grid, grid, 4, dim, str, box)) return 0;
+    }
+    auto kern = pull_pipe3d_kernel<ORDER, OP, NCW>;
+    IB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
+    const int nblocks = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    long long *dbg = nullptr;
+    if (getenv("IB200_PIPE_DEBUG")) IB200_CUDA_CHECK(cudaGetSymbolAddress((void **)&dbg, g_pipe_dbg));
+    kern<<<nblocks, 32 * (NCW + 1), smem_total, stream>>>(kp, tm_vol, tm_grid, vol, out, (int)ntiles, cmul, bmul, gbmul,
+        make_inv((kp.pts_n[2] + 31) / 32), make_inv((kp.pts_n[1] + 7) / 8), make_inv((kp.pts_n[0] + 7) / 8), dbg);
+    static thread_local char name[64];
+    snprintf(name, sizeof(name), "%s_pipe3d_o%d", OP == OP_GRAD ? "grad" : "pull", ORDER);
+    note_launch(name);
+    IB200_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out, cudaStream_t stream) {
+    if (op != OP_PULL && op != OP_GRAD) return 0;
+    if (dtype != IB200_F32) return 0;
+    if (kp.dim != 3 || !kp.pts_dense) return 0;
+    if (kp.order[0] != kp.order[1] || kp.order[0] != kp.order[2]) return 0;
+    if (kp.order[0] < 1 || kp.order[0] > 3) return 0;
+    if (kp.pts_total < 32768) return 0;
+    if (kp.pts_total * 3 > 0x7fffffffLL) return 0;
+    if (kp.flags & (IB200_FLAG_REF_LINEAR_GRAD_SIGN | IB200_FLAG_NO_PIPE)) return 0;
+    // TMA: unit innermost stride, 16-byte aligned bases and strides
+    if (kp.vol_s[2] != 1) return 0;
+    if ((uintptr_t)vol % 16 || (uintptr_t)grid % 16) return 0;
+    if (kp.vol_s[0] % 4 || kp.vol_s[1] % 4 || kp.vol_sb % 4 || kp.vol_sc % 4) return 0;
+    if (kp.pts_n[2] % 4 || kp.grid_sb % 4) return 0;
+    const float *v = (const float *)vol, *g = (const float *)grid;
+    float *o = (float *)out;
+    constexpr int NCW = 15;
+    if (op == OP_PULL) {
+        switch (kp.order[0]) {
+        case 1: return launch_pull_pipe<1, OP_PULL, NCW>(kp, v, g, o, stream);
+        case 2: return launch_pull_pipe<2, OP_PULL, NCW>(kp, v, g, o, stream);
+        case 3: return launch_pull_pipe<3, OP_PULL, NCW>(kp, v, g, o, stream);
+        }
+    } else {
+        switch (kp.order[0]) {
+        case 1: return launch_pull_pipe<1, OP_GRAD, NCW>(kp, v, g, o, stream);
+        case 2: return launch_pull_pipe<2, OP_GRAD, NCW>(kp, v, g, o, stream);
+        case 3: return launch_pull_pipe<3, OP_GRAD, NCW>(kp, v, g, o, stream);
+        }
+    }
+    return 0;
+}
+
+}  // namespace ib200
+
+// debugging aid (not part of the public ABI): phase timers of the last pipe launch
+extern "C" __attribute__((visibility("default"))) int ib200_debug_pipe_counters(long long *out16) {
+    return cudaMemcpyFromSymbol(out16, ib200::g_pipe_dbg, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}

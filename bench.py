@@ -46,46 +46,62 @@ def make_workload(size, device, seed=1234):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle-reason samples DURING the timed region, through NVML (a poll every ~2 ms;
+    the `nvidia-smi -lms` loop of the profiling recipe needs ~1 s to print its first line, longer
+    than the whole timed region)."""
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.samples, self.stop_flag, self.armed = index, [], False, False
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML indexes the board
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(',')[index])
+                except Exception:
+                    phys = index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '50'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.samples.append([x.strip() for x in line.split(',')])
-        except Exception:
-            pass
+        if self.nvml is None:
+            return
+        n = self.nvml
+        masks = [getattr(n, 'nvmlClocksEventReasonHwSlowdown', 0x8), getattr(n, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                 getattr(n, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), getattr(n, 'nvmlClocksEventReasonSwPowerCap', 0x4)]
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                if self.armed:
+                    self.samples.append((mhz, [bool(r & m) for m in masks]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc is not None:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
-                for n, v in zip(names, s[2:6]):
-                    if v.lower().startswith('active'):
-                        reasons.add(n)
-            except Exception:
-                continue
+        sm, reasons = [], set()
+        for mhz, flags in self.samples:
+            sm.append(mhz)
+            for nm, f in zip(self.NAMES, flags):
+                if f:
+                    reasons.add(nm)
         if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+            return {'sm_mhz': None, 'sm_max_mhz': getattr(self, 'sm_max', None), 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': self.sm_max, 'reasons': sorted(reasons),
                 'samples': len(sm)}
 
 
@@ -250,11 +266,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.15)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = ib.launch_count()
     barrier()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    sampler.armed = True
     t_start.record()
     for k in range(args.steps):
         ev[k][0].record()
@@ -264,6 +280,7 @@ def main():
         ev[k][2].record()
     t_end.record()
     barrier()
+    sampler.armed = False
     launches = ib.launch_count() - launches0
     clocks = sampler.finish() if rank == 0 else None
     total_ms = t_start.elapsed_time(t_end)

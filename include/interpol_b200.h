@@ -80,7 +80,9 @@ enum {
     IB200_FLAG_REF_LINEAR_GRAD_SIGN = 1u << 1,
     /* never take the persistent warp-specialised kernels (fall back to the one-tile-per-CTA
      * tiled kernels; A/B testing, profiling) */
-    IB200_FLAG_NO_PIPE = 1u << 2
+    IB200_FLAG_NO_PIPE = 1u << 2,
+    /* take the persistent kernels even for problems too small to amortise their ramp-up (tests) */
+    IB200_FLAG_FORCE_PIPE = 1u << 3
 };
 
 /*

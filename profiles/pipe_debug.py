@@ -31,3 +31,16 @@ items = max(buf[10], 1)
 print('order', order, 'C', C, 'bound', bound, 'kernel %.1f us' % (a.elapsed_time(b) * 1e3), ib.last_kernel(), 'items', items)
 for i, nm in enumerate(names):
     print('%-16s total %10d ticks   per item %8.0f' % (nm, buf[i], buf[i] / items))
+# ---- push ----
+img = vol
+for _ in range(3):
+    pp.grid_push(img, grid, [256] * 3, [bound], [order], 1)
+torch.cuda.synchronize()
+a.record(); pp.grid_push(img, grid, [256] * 3, [bound], [order], 1); b.record(); torch.cuda.synchronize()
+_lib.lib().ib200_debug_push_counters(buf)
+names = ['P wait bdone', 'P flush issue', 'P flush read', 'P wait kfull', 'C wait bfull', 'C zero', 'C cells', 'C scale', 'C atomics',
+         'C wait rows', 'C fold', 'C convert', 'C items', 'C whole loop']
+items = max(buf[12], 1)
+print('PUSH order', order, 'C', C, 'bound', bound, 'kernel %.1f us' % (a.elapsed_time(b) * 1e3), ib.last_kernel(), 'items', items)
+for i, nm in enumerate(names):
+    print('%-16s total %10d ticks   per item %8.0f' % (nm, buf[i], buf[i] / items))

@@ -101,7 +101,11 @@ struct PipeGeom {
                         // lies inside the volume (or whose bound is `zero`: the TMA fill is the answer)
     int zlo, zhi;       // lanes (z offsets inside the tile) this box serves
     int last;           // last part of its tile
+    int xfold;          // x-planes are requested through the boundary map of x
+    int zfold;          // z is stored FOLDED: lo[2] / ext[2] span the folded indices, taps go through a table
+    int za, zn;         // the table covers the unfolded indices [za, za + zn)
 };
+constexpr int kZLut = 128;   // longest unfolded z range a folded box may serve
 
 __device__ __forceinline__ int floor_div4(int a) { return a >> 2; }   // arithmetic shift == floor
 
@@ -184,9 +188,11 @@ __device__ __forceinline__ void pipe_quarter_boxes(const KParams &kp, const floa
 
 // geometry of the box of quarters [q0, q1) from the keys above
 template <int ORDER>
-__device__ __forceinline__ PipeGeom pipe_geom(const KParams &kp, const int *keys, int q0, int q1) {
+__device__ __forceinline__ PipeGeom pipe_geom(const KParams &kp, const int *keys, int q0, int q1, int max_x = kBoxX) {
     PipeGeom g;
+    g.xfold = 0; g.zfold = 0; g.za = 0; g.zn = 0;
     bool any = true;
+    bool zfit = true;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         int ka = kIntMax, kb = kIntMin;
@@ -195,12 +201,39 @@ __device__ __forceinline__ PipeGeom pipe_geom(const KParams &kp, const int *keys
         int a = 0, b = 0;
         if (fa > fc) any = false;
         else { a = start_of<ORDER>(fa); b = start_of<ORDER>(fc); }
+        if (d == 2 && any) {
+            // Mirror-type bounds along z: instead of staging out-of-volume words and rewriting them,
+            // stage the FOLDED index range (a sub-range of the volume, usually smaller) and let the taps
+            // look their word up in a small table (the producer fills it, pull_pipe.cu).
+            const int bz = kp.bound[2];
+            const bool mirror = bz == IB200_BOUND_REPLICATE || bz == IB200_BOUND_DCT1 || bz == IB200_BOUND_DCT2 ||
+                                bz == IB200_BOUND_DST1 || bz == IB200_BOUND_DST2;
+            const int lo_ok = bz == IB200_BOUND_DST1 ? 1 : 0;
+            const long long top = (long long)b + ORDER;
+            if (mirror && (a < lo_ok || top > kp.vol_n[2] - 1)) {
+                const long long len = top - a + 1;
+                if (len > kZLut) {
+                    zfit = false;
+                } else {
+                    const int lane = threadIdx.x & 31;
+                    int fmin = kIntMax, fmax = kIntMin;
+                    for (int e = lane; e < (int)len; e += 32) {
+                        const int f = bound_index<int>(bz, a + e, kp.vol_n[2]);
+                        fmin = min(fmin, f); fmax = max(fmax, f);
+                    }
+                    fmin = __reduce_min_sync(0xffffffffu, fmin);
+                    fmax = __reduce_max_sync(0xffffffffu, fmax);
+                    g.zfold = 1; g.za = a; g.zn = (int)len;
+                    a = fmin; b = fmax - ORDER;        // so that ext = fmax - (fmin & ~3) + 1 below
+                }
+            }
+        }
         if (d == 2) a &= ~3;
         g.lo[d] = a;
         const long long e = (long long)b - a + 1 + ORDER;
         g.ext[d] = (int)(e > 0x3fffffff ? 0x3fffffff : e);
     }
-    const bool fits = g.ext[0] <= kBoxX && g.ext[1] <= kBoxY && g.ext[2] <= kBoxZ;
+    const bool fits = zfit && g.ext[0] <= max_x && g.ext[1] <= kBoxY && g.ext[2] <= kBoxZ;
     if (!any) {
         g.mode = PIPE_EMPTY; g.ext[0] = g.ext[1] = g.ext[2] = 0; g.lo[0] = g.lo[1] = g.lo[2] = 0;
     } else if (!fits) {
@@ -213,7 +246,14 @@ __device__ __forceinline__ PipeGeom pipe_geom(const KParams &kp, const int *keys
     for (int d = 0; d < 3; ++d) {
         const int e = d == 2 ? vpr : min(g.ext[d], d == 0 ? kBoxX : kBoxY);
         int r0 = 0, r1 = e;
-        if (kp.bound[d] != IB200_BOUND_ZERO) {
+        // x: one TMA request per plane, so the producer simply requests the folded plane (bounds of sign +1)
+        const bool by_tma = d == 0 && (kp.bound[0] == IB200_BOUND_REPLICATE || kp.bound[0] == IB200_BOUND_DCT1 ||
+                                       kp.bound[0] == IB200_BOUND_DCT2 || kp.bound[0] == IB200_BOUND_DFT);
+        if (by_tma) {
+            g.xfold = (g.lo[0] < 0 || g.lo[0] + e > kp.vol_n[0]) ? 1 : 0;
+        } else if (d == 2 && g.zfold) {
+            // folded range: inside the volume by construction
+        } else if (kp.bound[d] != IB200_BOUND_ZERO) {
             const int lo_ok = (kp.bound[d] == IB200_BOUND_DST1) ? 1 : 0;     // dst1 zeroes voxel 0 (Q1)
             if (d == 2) {
                 // vectors whose four source voxels lie in [lo_ok, nz - 1]
@@ -232,42 +272,111 @@ __device__ __forceinline__ PipeGeom pipe_geom(const KParams &kp, const int *keys
     return g;
 }
 
-// Fix-up of a PIPE_FOLD box by `nthreads` (even) cooperating threads (thread `t`):
-// every vector with a source outside the volume along a non-zero-bound axis is recomputed through
-// the boundary maps.  Two threads share one (x, y) row of the box (even / odd vectors): a row
-// outside the volume in x or y is rewritten entirely, a row inside only where z leaves the volume.
-__device__ __forceinline__ void pipe_fixup(const KParams &kp, const PipeGeom &g, float *bx, const float *src, int t, int nthreads) {
+// Fix-up of x-plane `a` of a PIPE_FOLD box by one warp: every vector with a source outside the
+// volume along an axis whose fold the TMA requests did not already apply is recomputed through
+// the boundary maps.  The folded source usually lies inside the box itself (mirror / replicate
+// bounds next to a face): it is then read back from shared memory, otherwise from global memory.
+// Only in-range elements are ever read, only out-of-range elements are written: no hazard
+// between warps fixing different planes.
+__device__ __forceinline__ void pipe_fixup_plane(const KParams &kp, const PipeGeom &g, float *bx, const float *src, int a) {
+    const int lane = threadIdx.x & 31;
     const int vpr = (g.ext[2] + 3) >> 2;
-    const int zlo = kp.bound[2] == IB200_BOUND_DST1 ? 1 : 0;
-    for (int row = t >> 1; row < g.ext[0] * kBoxY; row += nthreads >> 1) {
-        const int a = row / kBoxY, bb = row % kBoxY;
-        if (bb >= g.ext[1]) continue;
-        const bool row_in = a >= g.r0[0] && a < g.r1[0] && bb >= g.r0[1] && bb < g.r1[1];
-        if (row_in && g.r0[2] == 0 && g.r1[2] == vpr) continue;
-        const int sx = g.lo[0] + a, sy = g.lo[1] + bb;
-        const int sgxy = bound_sign<int>(kp.bound[0], sx, kp.vol_n[0]) * bound_sign<int>(kp.bound[1], sy, kp.vol_n[1]);
-        const float *rowp = src + bound_index<int>(kp.bound[0], sx, kp.vol_n[0]) * (int)kp.vol_s[0] +
-                            bound_index<int>(kp.bound[1], sy, kp.vol_n[1]) * (int)kp.vol_s[1];
+    const int sx = g.lo[0] + a;
+    const int fx = bound_index<int>(kp.bound[0], sx, kp.vol_n[0]);
+    const int sgx = bound_sign<int>(kp.bound[0], sx, kp.vol_n[0]);
+    const bool x_in = a >= g.r0[0] && a < g.r1[0];
+    const int ax = x_in ? a : fx - g.lo[0];
+    const bool x_src = x_in || (ax >= g.r0[0] && ax < g.r1[0]);
+    const bool z_all = g.r0[2] == 0 && g.r1[2] == vpr;
+    for (int bb = lane >> 1; bb < g.ext[1]; bb += 16) {
+        const bool y_in = bb >= g.r0[1] && bb < g.r1[1];
+        if (x_in && y_in && z_all) continue;
+        const int sy = g.lo[1] + bb;
+        // (axes of bound `zero` count as in range -- the TMA fill is their answer -- but their sign is 0 outside)
+        const int fy = bound_index<int>(kp.bound[1], sy, kp.vol_n[1]);
+        const int sgxy = sgx * bound_sign<int>(kp.bound[1], sy, kp.vol_n[1]);
+        const int by = fy - g.lo[1];
+        const bool xy_src = x_src && by >= g.r0[1] && by < g.r1[1];
+        const float *brow = bx + ax * kBoxPlane + by * kBoxZ;
+        const float *grow = src + fx * (int)kp.vol_s[0] + fy * (int)kp.vol_s[1];
         float *dstrow = bx + a * kBoxPlane + bb * kBoxZ;
-        for (int v = (t & 1); v < vpr; v += 2) {
-            if (row_in && v >= g.r0[2] && v < g.r1[2]) continue;
-            const int sz = g.lo[2] + 4 * v;
-            float val[4] = {0.f, 0.f, 0.f, 0.f};
-            if (sgxy != 0) {
-                if (sz >= zlo && sz + 3 <= kp.vol_n[2] - 1) {
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(rowp + sz));      // sz % 4 == 0, rows 16-byte aligned
-                    val[0] = sgxy * q.x; val[1] = sgxy * q.y; val[2] = sgxy * q.z; val[3] = sgxy * q.w;
-                } else {
+        for (int v = lane & 1; v < vpr; v += 2) {
+            const bool v_in = v >= g.r0[2] && v < g.r1[2];
+            if (x_in && y_in && v_in) continue;
+            float val[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int sg = sgxy * bound_sign<int>(kp.bound[2], sz + k, kp.vol_n[2]);
-                        if (sg != 0) val[k] = (float)sg * __ldg(rowp + bound_index<int>(kp.bound[2], sz + k, kp.vol_n[2]));
-                    }
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int sz = g.lo[2] + 4 * v + k;
+                // a folded-z box holds RAW volume words (the taps apply the z map, dst1's zero at voxel 0 included)
+                const int fz = g.zfold ? min(sz, kp.vol_n[2] - 1) : bound_index<int>(kp.bound[2], sz, kp.vol_n[2]);
+                const int sg = g.zfold ? sgxy : sgxy * bound_sign<int>(kp.bound[2], sz, kp.vol_n[2]);
+                const int zz = fz - g.lo[2];
+                float t = 0.f;
+                if (sg != 0) t = (xy_src && zz >= 4 * g.r0[2] && zz < 4 * g.r1[2]) ? brow[zz] : __ldg(grow + fz);
+                val[k] = (float)sg * t;
             }
             *reinterpret_cast<float4 *>(dstrow + 4 * v) = make_float4(val[0], val[1], val[2], val[3]);
         }
     }
+}
+
+// Adjoint of pipe_fixup_plane for the scatter kernels: x-plane `a` of a box of fixed-point
+// accumulators.  Whatever was accumulated outside the volume (along an axis whose fold neither
+// the TMA clip, nor the x-plane coordinate, nor the z table already covers) is added, with its
+// sign, onto its folded target -- inside the box when the target sits there (integer shared
+// atomic, exact), in global memory otherwise -- and then cleared so that the flush adds nothing.
+__device__ __forceinline__ void push_fold_plane(const KParams &kp, const PipeGeom &g, int *bx, float *dst, int a, float inv) {
+    const int lane = threadIdx.x & 31;
+    const int vpr = (g.ext[2] + 3) >> 2;
+    const int sx = g.lo[0] + a;
+    const int fx = bound_index<int>(kp.bound[0], sx, kp.vol_n[0]);
+    const int sgx = bound_sign<int>(kp.bound[0], sx, kp.vol_n[0]);
+    const bool x_in = a >= g.r0[0] && a < g.r1[0];
+    const int ax = x_in ? a : fx - g.lo[0];
+    const bool x_dst = x_in || (ax >= g.r0[0] && ax < g.r1[0]);
+    const bool z_all = g.r0[2] == 0 && g.r1[2] == vpr;
+    for (int bb = lane >> 1; bb < g.ext[1]; bb += 16) {
+        const bool y_in = bb >= g.r0[1] && bb < g.r1[1];
+        if (x_in && y_in && z_all) continue;
+        const int sy = g.lo[1] + bb;
+        const int fy = bound_index<int>(kp.bound[1], sy, kp.vol_n[1]);
+        const int sgxy = sgx * bound_sign<int>(kp.bound[1], sy, kp.vol_n[1]);
+        const int by = fy - g.lo[1];
+        const bool xy_dst = x_dst && by >= g.r0[1] && by < g.r1[1];
+        int *brow = bx + ax * kBoxPlane + by * kBoxZ;
+        float *grow = dst + fx * (int)kp.vol_s[0] + fy * (int)kp.vol_s[1];
+        int *srcrow = bx + a * kBoxPlane + bb * kBoxZ;
+        for (int v = lane & 1; v < vpr; v += 2) {
+            const bool v_in = v >= g.r0[2] && v < g.r1[2];
+            if (x_in && y_in && v_in) continue;
+            const int4 iv = *reinterpret_cast<const int4 *>(srcrow + 4 * v);
+            if ((iv.x | iv.y | iv.z | iv.w) == 0) continue;
+            const int vals[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (vals[k] == 0) continue;
+                const int sz = g.lo[2] + 4 * v + k;
+                if (g.zfold && sz > kp.vol_n[2] - 1) continue;                 // padding of a folded box: never written
+                const int fz = g.zfold ? sz : bound_index<int>(kp.bound[2], sz, kp.vol_n[2]);
+                const int sg = g.zfold ? sgxy : sgxy * bound_sign<int>(kp.bound[2], sz, kp.vol_n[2]);
+                if (sg == 0) continue;
+                const int zz = fz - g.lo[2];
+                if (xy_dst && zz >= 4 * g.r0[2] && zz < 4 * g.r1[2]) atomicAdd(brow + zz, sg * vals[k]);
+                else atomicAdd(grow + fz, (float)(sg * vals[k]) * inv);
+            }
+            *reinterpret_cast<int4 *>(srcrow + 4 * v) = make_int4(0, 0, 0, 0);
+        }
+    }
+}
+
+static inline int pipe_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else n = kNumSMs;
+    }
+    return n;
 }
 
 // ---- host side: tensor maps ---------------------------------------------------

@@ -89,9 +89,13 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
     unsigned long long *gfull = bars, *gempty = bars + kNG, *bfull = bars + 2 * kNG, *bempty = bars + 2 * kNG + kNB;
     unsigned long long *kfull = bars + 2 * kNG + 2 * kNB;                               // [2] box of a tile reduced
     int *rowctr = reinterpret_cast<int *>(bars + 2 * kNG + 2 * kNB + 2);                // [kNB] next unclaimed z-row
-    int *keys_base = rowctr + kNB;                                                      // [2][6] boxes of tiles j, j+1 (+2 pad each)
+    int *fixctr = rowctr + kNB;                                                         // [kNB] next unclaimed fix-up plane
+    int *fixdone = fixctr + kNB;                                                        // [kNB] fixed planes
+    int *keys_base = fixdone + kNB;                                                      // [2][6] boxes of tiles j, j+1 (+2 pad each)
     int *qkeys = keys_base + 16;                                                        // [24] quarter boxes (rare)
     PipeGeom *planned = reinterpret_cast<PipeGeom *>(qkeys + 24);                       // [4] parts of the planned tile
+    int *zoff = reinterpret_cast<int *>(planned + 4);                                   // [kNB][kZLut] folded z word of an unfolded index
+    float *zsgn = reinterpret_cast<float *>(zoff + kNB * kZLut);                        // [kNB][kZLut] its sign
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -188,13 +192,23 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     TICK(t_i);
                     if (lane == 0) {
                         geoms[s] = g;
-                        rowctr[s] = 0;
+                        rowctr[s] = 0; fixctr[s] = 0; fixdone[s] = 0;
+                    }
+                    if (g.zfold) {
+                        for (int e = lane; e < g.zn; e += 32) {
+                            zoff[s * kZLut + e] = bound_index<int>(kp.bound[2], g.za + e, kp.vol_n[2]) - g.lo[2];
+                            zsgn[s * kZLut + e] = (float)bound_sign<int>(kp.bound[2], g.za + e, kp.vol_n[2]);
+                        }
+                    }
+                    if (lane == 0) {
                         if (g.mode == PIPE_PLAIN || g.mode == PIPE_FOLD) mbar_expect_tx(bfull + s, (unsigned)g.ext[0] * kBoxPlane * 4u);
                     }
                     __syncwarp();
-                    if ((g.mode == PIPE_PLAIN || g.mode == PIPE_FOLD) && lane < g.ext[0])
-                        tma_load_5d(box + (size_t)s * kBoxWords + lane * kBoxPlane, &tm_vol, g.lo[2], g.lo[1], g.lo[0] + lane,
+                    if ((g.mode == PIPE_PLAIN || g.mode == PIPE_FOLD) && lane < g.ext[0]) {
+                        const int px = g.xfold ? bound_index<int>(kp.bound[0], g.lo[0] + lane, kp.vol_n[0]) : g.lo[0] + lane;
+                        tma_load_5d(box + (size_t)s * kBoxWords + lane * kBoxPlane, &tm_vol, g.lo[2], g.lo[1], px,
                                     c * cmul, b * bmul, bfull + s);
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bfull + s);
                     TOCK(a_issue, t_i);
@@ -204,8 +218,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
         if (dbg && blockIdx.x == 0 && lane == 0) { dbg[0] = a_kfull; dbg[1] = a_plan; dbg[2] = a_grid; dbg[3] = a_bempty; dbg[4] = a_issue; }
     } else {
         // ================================ consumers ===============================
-        const int ct = threadIdx.x;
-        const bool masked = kp.extrapolate != 1;
+            const bool masked = kp.extrapolate != 1;
         for (int q = 0; q < 2 && q < my_tiles; ++q) {      // boxes of the first two tiles, cooperatively
             int b, x0, y0, z0;
             decode(q, b, x0, y0, z0);
@@ -250,8 +263,19 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     last = g.last != 0;
                     float *bx = box + (size_t)s * kBoxWords;
                     if (g.mode == PIPE_FOLD) {
-                        pipe_fixup(kp, g, bx, src, ct, NCT);
-                        named_bar_sync(1, NCT);
+                        // x-planes are fixed by whichever warps get here first; nobody waits for a late warp,
+                        // only for the planes still being fixed
+                        for (;;) {
+                            int a = 0;
+                            if (lane == 0) a = atomicAdd(fixctr + s, 1);
+                            a = __shfl_sync(0xffffffffu, a, 0);
+                            if (a >= g.ext[0]) break;
+                            pipe_fixup_plane(kp, g, bx, src, a);
+                            __syncwarp();
+                            if (lane == 0) { __threadfence_block(); atomicAdd(fixdone + s, 1); }
+                        }
+                        while (*reinterpret_cast<volatile int *>(fixdone + s) < g.ext[0]) {}
+                        __threadfence_block();
                     }
                     TOCK(a_fix, t_f);
                     TICK(t_r);
@@ -294,7 +318,21 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                                         fast_dweights<ORDER>(cc[1] - f1, gy);
                                         fast_dweights<ORDER>(cc[2] - f2, gz);
                                     }
-                                    const float *ri = bx + ((int)f0 - g.lo[0]) * kBoxPlane + ((int)f1 - g.lo[1]) * kBoxZ + ((int)f2 - g.lo[2]);
+                                    const float *rxy = bx + ((int)f0 - g.lo[0]) * kBoxPlane + ((int)f1 - g.lo[1]) * kBoxZ;
+                                    const float *rk[W];
+                                    if (g.zfold) {
+                                        const int e0 = s * kZLut + (int)f2 - g.za;
+#pragma unroll
+                                        for (int k = 0; k < W; ++k) {
+                                            rk[k] = rxy + zoff[e0 + k];
+                                            const float sg = zsgn[e0 + k];
+                                            wz[k] *= sg;
+                                            if (GRAD) gz[k] *= sg;
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < W; ++k) rk[k] = rxy + ((int)f2 - g.lo[2]) + k;
+                                    }
                                     float acc = 0.f, ax_ = 0.f, ay_ = 0.f, az_ = 0.f;
 #pragma unroll
                                     for (int i = 0; i < W; ++i) {
@@ -304,7 +342,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                                             float t0 = 0.f, t1 = 0.f;
 #pragma unroll
                                             for (int k = 0; k < W; ++k) {
-                                                const float v = ri[i * kBoxPlane + jj * kBoxZ + k];
+                                                const float v = rk[k][i * kBoxPlane + jj * kBoxZ];
                                                 t0 = fmaf(wz[k], v, t0);
                                                 if (GRAD) t1 = fmaf(gz[k], v, t1);
                                             }
@@ -355,21 +393,11 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
 
 // ---------------------------------------------------------------- launch --
 
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-        else n = kNumSMs;
-    }
-    return n;
-}
-
 template <int ORDER, int OP, int NCW>
 static int launch_pull_pipe(const KParams &kp, const float *vol, const float *grid, float *out, cudaStream_t stream) {
     constexpr int NPT = 8 * 8 * 32;
     const size_t smem_total = (size_t)kNB * kBoxWords * 4 + (size_t)kNG * NPT * 3 * 4 + kNB * sizeof(PipeGeom) +
-                              (2 * kNG + 2 * kNB + 2) * sizeof(unsigned long long) + (kNB + 40) * sizeof(int) + 4 * sizeof(PipeGeom) + 64;
+                              (2 * kNG + 2 * kNB + 2) * sizeof(unsigned long long) + (3 * kNB + 40) * sizeof(int) + 4 * sizeof(PipeGeom) + (size_t)kNB * kZLut * 8 + 64;
     const i64 ntiles = kp.batch * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
     if (ntiles == 0) return 1;
     if (ntiles * kp.channels > 0x3fffffffLL) return 0;
@@ -394,7 +422,7 @@ static int launch_pull_pipe(const KParams &kp, const float *vol, const float *gr
     }
     auto kern = pull_pipe3d_kernel<ORDER, OP, NCW>;
     IB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
-    const int nblocks = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    const int nblocks = (int)(ntiles < pipe_sm_count() ? ntiles : pipe_sm_count());
     long long *dbg = nullptr;
     if (getenv("IB200_PIPE_DEBUG")) IB200_CUDA_CHECK(cudaGetSymbolAddress((void **)&dbg, g_pipe_dbg));
     kern<<<nblocks, 32 * (NCW + 1), smem_total, stream>>>(kp, tm_vol, tm_grid, vol, out, (int)ntiles, cmul, bmul, gbmul,
@@ -415,6 +443,12 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
     if (kp.pts_total < 32768) return 0;
     if (kp.pts_total * 3 > 0x7fffffffLL) return 0;
     if (kp.flags & (IB200_FLAG_REF_LINEAR_GRAD_SIGN | IB200_FLAG_NO_PIPE)) return 0;
+    // the pipeline needs a dozen (tile, channel) items per CTA to amortise its ramp-up (128^3 C=1: 7 per
+    // CTA, 0.20 ms against 0.10 ms for the one-tile-per-CTA kernel); IB200_FLAG_FORCE_PIPE overrides (tests)
+    {
+        const i64 items = kp.batch * kp.channels * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
+        if (items < 12 * (i64)pipe_sm_count() && !(kp.flags & IB200_FLAG_FORCE_PIPE)) return 0;
+    }
     // TMA: unit innermost stride, 16-byte aligned bases and strides
     if (kp.vol_s[2] != 1) return 0;
     if ((uintptr_t)vol % 16 || (uintptr_t)grid % 16) return 0;

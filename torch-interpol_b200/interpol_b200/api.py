@@ -41,7 +41,18 @@ def _stage(*tensors):
         dev = torch.device('cuda', torch.cuda.current_device())
     staged = tuple(None if t is None else (t if t.is_cuda else t.to(dev, non_blocking=True))
                    for t in tensors)
-    return staged, (lambda out: out.cpu())
+
+    def back(out):
+        if out.requires_grad or out.numel() == 0:
+            return out.cpu()
+        # page-locked result (recycled by torch's caching host allocator): the device->host copy runs
+        # at PCIe speed, and a result fed back into the next call uploads at PCIe speed as well
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(out.device).synchronize()
+        return host
+
+    return staged, back
 
 
 # --------------------------------------------------------------------------

@@ -33,6 +33,7 @@ for i, nm in enumerate(names):
     print('%-16s total %10d ticks   per item %8.0f' % (nm, buf[i], buf[i] / items))
 # ---- push ----
 img = vol
+pp.flags = 8
 for _ in range(3):
     pp.grid_push(img, grid, [256] * 3, [bound], [order], 1)
 torch.cuda.synchronize()

@@ -201,14 +201,15 @@ def test_pipe_push_full_size_adjoint():
     for bound in ([3], [6], [0], [1, 2, 4]):
         px = pp.grid_pull(vol, grid, bound, [3], 1)
         assert ib.last_kernel().startswith('pull_pipe3d')
-        py = pp.grid_push(y, grid, [256] * 3, bound, [3], 1)
+        py = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_push(y, grid, [256] * 3, bound, [3], 1))
         assert ib.last_kernel().startswith('push_pipe3d')
         lhs = (px.double() * y.double()).sum().item()
         rhs = (vol.double() * py.double()).sum().item()
         scale = (px.double().abs() * y.double().abs()).sum().item()
         assert abs(lhs - rhs) <= 5e-6 * scale, (bound, lhs, rhs, scale)
-    cnt = pp.grid_count(grid, [256] * 3, [6], [3], 1)
+    cnt = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_count(grid, [256] * 3, [6], [3], 1))
     assert ib.last_kernel().startswith('count_pipe3d')
     assert abs(cnt.double().sum().item() - 256 ** 3) <= 1e-6 * 256 ** 3
-    ref = _with_flags(pp, NO_PIPE, lambda: pp.grid_count(grid, [256] * 3, [6], [3], 1))
+    ref = pp.grid_count(grid, [256] * 3, [6], [3], 1)
+    assert ib.last_kernel().startswith('count_tile3d')
     assert rel_err(to_np(cnt), to_np(ref)) <= 4e-6

@@ -102,6 +102,9 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
         tma_prefetch_desc(&tm_grid);
     }
     if (threadIdx.x < 16) keys_base[threadIdx.x] = pipe_key_init(threadIdx.x);
+    // boxes and cell sums start clean; afterwards whoever flushes a plane re-zeroes it
+    for (int e = threadIdx.x; e < kPNB * kPBoxWords / 4; e += blockDim.x) reinterpret_cast<int4 *>(box)[e] = make_int4(0, 0, 0, 0);
+    for (int e = threadIdx.x; e < kCells; e += blockDim.x) cells[e] = 0;
     __syncthreads();
 
     const int ntx = (kp.pts_n[0] + TX - 1) / TX, nty = (kp.pts_n[1] + TY - 1) / TY, ntz = (kp.pts_n[2] + TZ - 1) / TZ;
@@ -126,47 +129,14 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                 mbar_arrive(gfull + s);
             }
         };
-        // flush item m (tile batch index fb, channel fc, geometry still in geoms[m % 2]) and wait until the
-        // TMA unit has read the box, so that the slot can be reopened
+        // item m is finished when every consumer warp has converted, flushed (and re-zeroed) its planes of the box
         long long p_wait = 0, p_issue = 0, p_read = 0, p_kfull = 0;
         auto flush = [&](int m, int fb, int fc) {
             const int s = m % kPNB;
             PTICK(t_w);
             mbar_wait(bdone + s, (m / kPNB) & 1);
             PTOCK(p_wait, t_w);
-            PTICK(t_f);
-            const PipeGeom g = geoms[s];
-            if (g.mode == PIPE_PLAIN || g.mode == PIPE_FOLD) {
-                const int *bxs = box + (size_t)s * kPBoxWords;
-                if (g.lo[1] >= 0 && g.lo[2] >= 0) {
-                    // one tensor reduction per x-plane; the TMA unit clips what overhangs the upper faces.
-                    // (It TRAPS on negative start coordinates -- profiles/micro/tma_reduce_micro.cu -- hence the branch.)
-                    if (lane < g.ext[0]) {
-                        const int px = g.xfold ? bound_index<int>(kp.bound[0], g.lo[0] + lane, kp.vol_n[0]) : g.lo[0] + lane;
-                        if (px >= 0 && px < kp.vol_n[0])
-                            tma_reduce_add_5d(&tm_out, bxs + lane * kBoxPlane, g.lo[2], g.lo[1], px, fc, fb);
-                    }
-                } else {
-                    // box hanging over a lower face (bound `zero` / `dft`, or y): one 1-D bulk reduction per row, clipped by hand
-                    float *dstv = out + ((i64)fb * kp.channels + fc) * kp.vol_total;
-                    const int zs = max(g.lo[2], 0), ze = min(g.lo[2] + kBoxZ, kp.vol_n[2]);
-                    const int nrows = g.ext[0] * kBoxY;
-                    for (int r = lane; r < nrows; r += 32) {
-                        const int a = r / kBoxY, bb = r - a * kBoxY;
-                        const int px = g.xfold ? bound_index<int>(kp.bound[0], g.lo[0] + a, kp.vol_n[0]) : g.lo[0] + a;
-                        const int sy = g.lo[1] + bb;
-                        if (bb < g.ext[1] && px >= 0 && px < kp.vol_n[0] && sy >= 0 && sy < kp.vol_n[1] && ze > zs)
-                            bulk_red_add_f32(dstv + ((i64)px * kp.vol_n[1] + sy) * kp.vol_n[2] + zs,
-                                             bxs + a * kBoxPlane + bb * kBoxZ + (zs - g.lo[2]), (unsigned)(ze - zs) * 4u);
-                    }
-                }
-            }
-            bulk_commit();
-            PTOCK(p_issue, t_f);
-            PTICK(t_r);
-            bulk_wait_read<0>();
-            __syncwarp();
-            PTOCK(p_read, t_r);
+            (void)fb; (void)fc; (void)p_issue; (void)p_read;
         };
         for (int q = 0; q < LA && q < my_tiles; ++q) request_grid(q);
         int n = 0;                                   // item sequence number
@@ -231,7 +201,6 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
         // drain: the last items
         if (kPNB >= 2 && n >= 2) flush(n - 2, ppb, ppc);
         if (n >= 1) flush(n - 1, pb, pc);
-        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
         if (dbg && blockIdx.x == 0 && lane == 0) { dbg[0] = p_wait; dbg[1] = p_issue; dbg[2] = p_read; dbg[3] = p_kfull; }
     } else {
         // ================================ consumers ===============================
@@ -309,8 +278,7 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     for (int u = 0; u < URW; ++u) rval[u] = COUNT ? 1.f : 0.f;
                     PTICK(t1);
                     if (boxed) {
-                        // ---- Z. values of this warp's rows (kept in registers), zero the accumulators (whole planes)
-                        //         and the cell sums, max |value| ----
+                        // ---- Z. values of this warp's rows (kept in registers), max |value| ----
                         float vm = 0.f;
 #pragma unroll
                         for (int u = 0; u < URW; ++u) {
@@ -319,17 +287,6 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                             rval[u] = COUNT ? 1.f : 0.f;
                             if (!COUNT && r < NROWS && p < nxv && ly < nyv && lane_ok) rval[u] = __ldg(src + (p * kp.pts_n[1] + ly) * kp.pts_n[2] + lane);
                         }
-                        for (;;) {
-                            const int a = claim(&ct->zero_next);
-                            if (a > g.ext[0]) break;
-                            if (a < g.ext[0]) {
-                                int4 *p4 = reinterpret_cast<int4 *>(bx + a * kBoxPlane);
-                                for (int e = lane; e < kBoxPlane / 4; e += 32) p4[e] = make_int4(0, 0, 0, 0);
-                            } else {
-                                for (int e = lane; e < nc0 * nc1 * nc2; e += 32) cells[e] = 0;
-                            }
-                            finish(&ct->zero_done);
-                        }
 #pragma unroll
                         for (int u = 0; u < URW; ++u) { const float av = fabsf(rval[u]); vm = fmaxf(vm, av < 3e38f ? av : 3e38f); }
                         {
@@ -337,7 +294,6 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                             if (lane == 0 && m != 0u) atomicMax(&ct->vmax_bits, m);
                         }
                         finish(&ct->bound_done);
-                        spin_until(&ct->zero_done, g.ext[0] + 1);
                         spin_until(&ct->bound_done, NCW);
                         const float vmax = __uint_as_float(*reinterpret_cast<volatile unsigned *>(&ct->vmax_bits));
                         PTOCK(c_z, t1);
@@ -503,18 +459,42 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                         }
                         PTOCK(c_f, t6);
                         PTICK(t7);
-                        // ---- C. fixed -> float in place ----
+                        // ---- C. per x-plane, by the warp that claims it: fixed -> float in place, flush through the
+                        //         TMA unit (float add; folds along x go into the plane coordinate, what overhangs an
+                        //         upper face is clipped), wait until the plane has been read, zero it for the next item ----
+                        const bool by_tensor = g.lo[1] >= 0 && g.lo[2] >= 0;     // the TMA unit TRAPS on negative start coordinates
+                        const int zs = max(g.lo[2], 0), ze = min(g.lo[2] + kBoxZ, kp.vol_n[2]);
                         for (;;) {
                             const int a = claim(&ct->conv_next);
                             if (a >= g.ext[0]) break;
                             int4 *p4 = reinterpret_cast<int4 *>(bx + a * kBoxPlane);
-                            for (int e = lane; e < kBoxPlane / 4; e += 32) {
-                                const int4 iv = p4[e];
-                                float4 fv = make_float4(inv * (float)iv.x, inv * (float)iv.y, inv * (float)iv.z, inv * (float)iv.w);
-                                *reinterpret_cast<float4 *>(p4 + e) = fv;
+                            const int px = g.xfold ? bound_index<int>(kp.bound[0], g.lo[0] + a, kp.vol_n[0]) : g.lo[0] + a;
+                            const bool px_ok = px >= 0 && px < kp.vol_n[0];
+                            if (scale != 0.f && px_ok) {
+                                for (int e = lane; e < kBoxPlane / 4; e += 32) {
+                                    const int4 iv = p4[e];
+                                    *reinterpret_cast<float4 *>(p4 + e) = make_float4(inv * (float)iv.x, inv * (float)iv.y, inv * (float)iv.z, inv * (float)iv.w);
+                                }
+                                fence_async_smem();
+                                __syncwarp();
+                                if (by_tensor) {
+                                    if (lane == 0) tma_reduce_add_5d(&tm_out, p4, g.lo[2], g.lo[1], px, c, b);
+                                } else if (lane < g.ext[1] && ze > zs) {
+                                    // box hanging over a lower face (bound `zero` / `dft`, or y): one 1-D bulk reduction per row, clipped by hand
+                                    const int sy = g.lo[1] + lane;
+                                    if (sy >= 0 && sy < kp.vol_n[1])
+                                        bulk_red_add_f32(dst + ((i64)px * kp.vol_n[1] + sy) * kp.vol_n[2] + zs,
+                                                         bx + a * kBoxPlane + lane * kBoxZ + (zs - g.lo[2]), (unsigned)(ze - zs) * 4u);
+                                }
+                                bulk_commit();
+                                bulk_wait_read<0>();
+                                __syncwarp();
                             }
+                            if (scale != 0.f)
+                                for (int e = lane; e < kBoxPlane / 4; e += 32) p4[e] = make_int4(0, 0, 0, 0);
+                            if (a == 0)
+                                for (int e = lane; e < nc0 * nc1 * nc2; e += 32) cells[e] = 0;
                         }
-                        fence_async_smem();
                         PTOCK(c_c, t7);
                     }
                     c_items += 1;
@@ -527,6 +507,7 @@ push_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                 } while (!last);
             }
         }
+        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");       // every reduction this thread issued has landed
         if (dbg && blockIdx.x == 0 && warp == 0 && lane == 0) {
             dbg[4] = c_bfull; dbg[5] = c_z; dbg[6] = c_h; dbg[7] = c_s; dbg[8] = c_a; dbg[9] = c_aw; dbg[10] = c_f; dbg[11] = c_c;
             dbg[12] = c_items; dbg[13] = clock64() - t_all;

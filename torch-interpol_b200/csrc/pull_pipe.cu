@@ -443,11 +443,13 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
     if (kp.pts_total < 32768) return 0;
     if (kp.pts_total * 3 > 0x7fffffffLL) return 0;
     if (kp.flags & (IB200_FLAG_REF_LINEAR_GRAD_SIGN | IB200_FLAG_NO_PIPE)) return 0;
-    // the pipeline needs a dozen (tile, channel) items per CTA to amortise its ramp-up (128^3 C=1: 7 per
-    // CTA, 0.20 ms against 0.10 ms for the one-tile-per-CTA kernel); IB200_FLAG_FORCE_PIPE overrides (tests)
-    {
-        const i64 items = kp.batch * kp.channels * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
-        if (items < 12 * (i64)pipe_sm_count() && !(kp.flags & IB200_FLAG_FORCE_PIPE)) return 0;
+    // The pipeline needs a dozen tiles per CTA to amortise its ramp-up (128^3: 7 per CTA, 0.20 ms against
+    // 0.10 ms for the one-tile-per-CTA kernel), and with several channels the tile kernel, which shares one
+    // plan and one staged grid tile between the channels of a tile, is still 3-7 % ahead (256^3 C=4: pull 1.13
+    // vs 1.17 ms, grad 1.34 vs 1.44 ms).  IB200_FLAG_FORCE_PIPE overrides (tests, profiling).
+    if (!(kp.flags & IB200_FLAG_FORCE_PIPE)) {
+        const i64 tiles = kp.batch * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
+        if (tiles < 12 * (i64)pipe_sm_count() || kp.channels > 1) return 0;
     }
     // TMA: unit innermost stride, 16-byte aligned bases and strides
     if (kp.vol_s[2] != 1) return 0;

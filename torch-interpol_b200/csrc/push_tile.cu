@@ -28,7 +28,7 @@
 
 namespace ib200 {
 
-constexpr int kHist = 4096;            // coarse cells available for the overflow bound
+constexpr int kHist = 1024;            // coarse cells available for the overflow bound
 constexpr float kMagic = 12582912.f;   // 1.5 * 2^23: float -> int by mantissa alignment
 constexpr int kMagicBits = 0x4B400000;
 

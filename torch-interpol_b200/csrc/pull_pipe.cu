@@ -334,6 +334,27 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                                         for (int k = 0; k < W; ++k) rk[k] = rxy + ((int)f2 - g.lo[2]) + k;
                                     }
                                     float acc = 0.f, ax_ = 0.f, ay_ = 0.f, az_ = 0.f;
+                                    if constexpr (!GRAD && W % 2 == 0) {
+                                        // packed FFMA2 (sm_100): rows j, j+1 of a plane share the z weights, so each
+                                        // instruction advances two row sums; 11 instructions per plane instead of 21
+                                        float2 wz2[W], acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                                        for (int k = 0; k < W; ++k) wz2[k] = make_float2(wz[k], wz[k]);
+#pragma unroll
+                                        for (int i = 0; i < W; ++i) {
+                                            float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+                                            for (int jj = 0; jj < W; jj += 2) {
+                                                float2 t2 = make_float2(0.f, 0.f);
+#pragma unroll
+                                                for (int k = 0; k < W; ++k)
+                                                    t2 = __ffma2_rn(wz2[k], make_float2(rk[k][i * kBoxPlane + jj * kBoxZ], rk[k][i * kBoxPlane + (jj + 1) * kBoxZ]), t2);
+                                                s2 = __ffma2_rn(make_float2(wy[jj], wy[jj + 1]), t2, s2);
+                                            }
+                                            acc2 = __ffma2_rn(make_float2(wx[i], wx[i]), s2, acc2);
+                                        }
+                                        acc = acc2.x + acc2.y;
+                                    } else {
 #pragma unroll
                                     for (int i = 0; i < W; ++i) {
                                         float s00 = 0.f, s10 = 0.f, s01 = 0.f;
@@ -351,6 +372,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                                         }
                                         if (!GRAD) acc = fmaf(wx[i], s00, acc);
                                         else { ax_ = fmaf(gx[i], s00, ax_); ay_ = fmaf(wx[i], s10, ay_); az_ = fmaf(wx[i], s01, az_); }
+                                    }
                                     }
                                     if (!GRAD) res[0] = acc;
                                     else { res[0] = ax_; res[1] = ay_; res[2] = az_; }

@@ -25,11 +25,12 @@ __device__ __forceinline__ void fast_weights(float t, float (&w)[ORDER + 1]) {
         w[2] = 0.5f * c * c;
     } else if constexpr (ORDER == 3) {
         // t in [1, 2]: |x| = t (outer), t-1 (inner), 2-t (inner), 3-t (outer)
-        const float a = 2.f - t, x1 = t - 1.f;
-        w[0] = a * a * a * (1.f / 6.f);
-        w[1] = (x1 * x1 * (x1 - 2.f) * 3.f + 4.f) * (1.f / 6.f);
-        w[2] = (a * a * (a - 2.f) * 3.f + 4.f) * (1.f / 6.f);
-        w[3] = x1 * x1 * x1 * (1.f / 6.f);
+        // u = t - 1 in [0, 1], a = 1 - u:  u^3/6, (3u^3 - 6u^2 + 4)/6 and their mirror images, in FMA form
+        const float u = t - 1.f, a = 2.f - t, u2 = u * u, a2 = a * a;
+        w[0] = a2 * (a * (1.f / 6.f));
+        w[1] = fmaf(u2, fmaf(u, 0.5f, -1.f), 2.f / 3.f);
+        w[2] = fmaf(a2, fmaf(a, 0.5f, -1.f), 2.f / 3.f);
+        w[3] = u2 * (u * (1.f / 6.f));
     } else {
 #pragma unroll
         for (int k = 0; k <= ORDER; ++k) {

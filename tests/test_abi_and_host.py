@@ -210,3 +210,29 @@ def test_install_as_backend_seam():
         assert shim.grid_pull is ib.grid_pull and shim.restrict is ib.restrict
     finally:
         del sys.modules['fake_interpol'], sys.modules['fake_interpol.api']
+
+
+def test_pinned_result_pool_reuses_released_buffers(monkeypatch):
+    """api._pinned_empty hands a page-locked buffer out again only after the caller dropped every
+    view of it (host logic; the page-locking itself is stubbed out: no CUDA here)."""
+    import torch
+    import interpol_b200.api as api
+    real_empty = torch.empty
+
+    def fake_empty(*a, **k):
+        k.pop('pin_memory', None)
+        return real_empty(*a, **k)
+    monkeypatch.setattr(torch, 'empty', fake_empty)
+    monkeypatch.setattr(api, '_POOL', [])
+    a = api._pinned_empty([4, 5], torch.float32)
+    pa = a.data_ptr()
+    b = api._pinned_empty([4, 5], torch.float32)
+    assert b.data_ptr() != pa                       # `a` is still alive
+    view = a[1:]
+    del a
+    c = api._pinned_empty([4, 5], torch.float32)
+    assert c.data_ptr() not in (pa,)                # a view of `a` is still alive
+    del view
+    d = api._pinned_empty([2, 5], torch.float64)
+    assert d.data_ptr() == pa and d.shape == (2, 5) and d.dtype == torch.float64
+    assert len(api._POOL) == 3

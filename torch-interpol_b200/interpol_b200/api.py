@@ -8,6 +8,8 @@ in place on that device; CPU tensors are staged to the current CUDA device
 (asynchronously when pinned), processed by the same kernels and returned on
 the CPU -- there is no CPU implementation.
 """
+import threading
+
 import torch
 
 from .utils import expanded_shape, matvec, meshgrid_ij
@@ -25,6 +27,35 @@ __all__ = [
 # --------------------------------------------------------------------------
 # host <-> device staging
 # --------------------------------------------------------------------------
+
+# Page-locking a fresh 64 MB buffer costs ~11 ms (cudaHostAlloc; measured, profiles/xfer_rates.py) -- ten
+# times the copy it serves -- so result buffers come from a small pool and are handed out again once the
+# caller has dropped every tensor that views them (storage use count back to the pool's own reference).
+_POOL, _POOL_LOCK, _POOL_MAX_BYTES = [], threading.Lock(), 4 << 30
+
+
+def _pinned_empty(shape, dtype):
+    use_count = getattr(torch._C, '_storage_Use_Count', None)
+    nbytes = 1
+    for n in shape:
+        nbytes *= int(n)
+    nbytes *= torch.empty(0, dtype=dtype).element_size()
+    if use_count is None or nbytes == 0:
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+    with _POOL_LOCK:
+        best = None
+        for buf in _POOL:
+            if buf.numel() >= nbytes and (best is None or buf.numel() < best.numel()) \
+                    and use_count(buf.untyped_storage()._cdata) <= 2:
+                best = buf
+        if best is None:
+            total = sum(b.numel() for b in _POOL)
+            while _POOL and total + nbytes > _POOL_MAX_BYTES:
+                total -= _POOL.pop(0).numel()
+            best = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            _POOL.append(best)
+        return best[:nbytes].view(dtype).view(list(shape))
+
 
 def _stage(*tensors):
     """Move CPU tensors to the current CUDA device.  Returns (tensors, back)
@@ -45,9 +76,9 @@ def _stage(*tensors):
     def back(out):
         if out.requires_grad or out.numel() == 0:
             return out.cpu()
-        # page-locked result (recycled by torch's caching host allocator): the device->host copy runs
-        # at PCIe speed, and a result fed back into the next call uploads at PCIe speed as well
-        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        # page-locked result: the device->host copy runs at PCIe speed, and a result fed back into the
+        # next call uploads at PCIe speed as well
+        host = _pinned_empty(out.shape, out.dtype)
         host.copy_(out, non_blocking=True)
         torch.cuda.current_stream(out.device).synchronize()
         return host

@@ -354,6 +354,28 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                                             acc2 = __ffma2_rn(make_float2(wx[i], wx[i]), s2, acc2);
                                         }
                                         acc = acc2.x + acc2.y;
+                                    } else if constexpr (GRAD) {
+                                        // packed FFMA2: (value, d/dz) share the tap, (value, d/dy) share the row sum
+                                        float2 wgz[W];
+#pragma unroll
+                                        for (int k = 0; k < W; ++k) wgz[k] = make_float2(wz[k], gz[k]);
+#pragma unroll
+                                        for (int i = 0; i < W; ++i) {
+                                            float2 s2 = make_float2(0.f, 0.f);      // (s00, s10)
+                                            float s01 = 0.f;
+#pragma unroll
+                                            for (int jj = 0; jj < W; ++jj) {
+                                                float2 t2 = make_float2(0.f, 0.f);  // (t0, t1)
+#pragma unroll
+                                                for (int k = 0; k < W; ++k) {
+                                                    const float v = rk[k][i * kBoxPlane + jj * kBoxZ];
+                                                    t2 = __ffma2_rn(wgz[k], make_float2(v, v), t2);
+                                                }
+                                                s2 = __ffma2_rn(make_float2(wy[jj], gy[jj]), make_float2(t2.x, t2.x), s2);
+                                                s01 = fmaf(wy[jj], t2.y, s01);
+                                            }
+                                            ax_ = fmaf(gx[i], s2.x, ax_); ay_ = fmaf(wx[i], s2.y, ay_); az_ = fmaf(wx[i], s01, az_);
+                                        }
                                     } else {
 #pragma unroll
                                     for (int i = 0; i < W; ++i) {

@@ -164,6 +164,18 @@ IB200_API int ib200_spline_coeff(void *data, int32_t dtype, int64_t outer, int64
                        int64_t inner, int32_t bound, int32_t order,
                        int32_t device, void *stream);
 
+/* Separable resampling along one axis of a dense tensor viewed as (outer, n_in, inner):
+ * out (outer, n_out, inner)[o, i, j] = sum_k w_k(coords[i]) * in[o, fold(start + k), j].
+ * One call per axis replaces the dense-grid construction + grid_pull of interpol.resize
+ * (interpol/resize.py:91-117; plugin seam interpol/jitfields.py:95): the sampling grid of a resize is
+ * the tensor product of one coordinate vector per axis.  `coords` (n_out values, same dtype as the
+ * data, voxel units of the input axis) are those vectors; `all_nearest` / `all_linear` tell whether
+ * EVERY axis of the N-D call has order 0 / 1 (iso0.py:12 rounding, iso1.py closed forms). */
+IB200_API int ib200_resample_axis(const void *in, void *out, const void *coords, int32_t dtype,
+                        int64_t outer, int64_t n_in, int64_t n_out, int64_t inner,
+                        int32_t order, int32_t bound, int32_t extrapolate,
+                        int32_t all_nearest, int32_t all_linear, int32_t device, void *stream);
+
 /* Introspection */
 IB200_API int ib200_abi_version(void);
 IB200_API const char *ib200_error_string(int status);

@@ -118,3 +118,48 @@ def test_coeff_unsupported_bound():
     for b in (4, 5):
         with pytest.raises(NotImplementedError):
             oracle.spline_coeff(x, b, 3, dim=1)
+
+
+def test_oracle_reproduces_reference_resize():
+    """`resize` = prefilter + pull on the tensor-product grid of per-axis coordinates: the oracle, fed
+    that grid, reproduces the reference's own resize outputs (tests/golden/resize.npz)."""
+    import os
+    import sys
+    import torch
+    import oracle
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    sys.path.insert(0, here)
+    import make_golden_resize as mg
+    gold = np.load(os.path.join(here, 'resize.npz'))
+    codes = {'zero': 0, 'nearest': 1, 'replicate': 1, 'dct1': 2, 'dct2': 3, 'dst1': 4, 'dst2': 5, 'dft': 6}
+
+    def aslist(v, n):
+        v = list(v) if isinstance(v, (list, tuple)) else [v]
+        return v + v[-1:] * (n - len(v))
+
+    for i, c in enumerate(mg.CASES):
+        if i % 5:
+            continue
+        want = gold['case%d' % i]
+        dim = len(c['shape'])
+        x = mg.make_input(i, c['shape']).numpy()
+        outshape = want.shape[2:]
+        lin = []
+        for a, f, n_in, n_out in zip(aslist(c['anchor'], dim), aslist(c['factor'], dim), c['shape'], outshape):
+            a = a[0]
+            if a == 'c':
+                lin.append(torch.linspace(0, n_in - 1, n_out, dtype=torch.float64).numpy())
+            elif a == 'e':
+                scale = n_in / n_out
+                lin.append(np.arange(n_out, dtype=np.float64) * scale + 0.5 * (scale - 1))
+            elif a == 'f':
+                lin.append(np.arange(n_out, dtype=np.float64) / f)
+            else:
+                lin.append(np.arange(n_out, dtype=np.float64) / f + ((n_in - 1) - (n_out - 1) / f))
+        grid = np.stack(np.meshgrid(*lin, indexing='ij'), axis=-1)[None]
+        order = aslist(c['order'], dim)
+        bound = [codes[b] for b in aslist(c['bound'], dim)]
+        coef = oracle.spline_coeff_nd(x, bound, order, dim) if c['prefilter'] else x
+        got = oracle.grid_pull(coef, grid, bound, order, int(c['extrapolate']))
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 1e-10 * max(scale, 1e-300), (i, c)

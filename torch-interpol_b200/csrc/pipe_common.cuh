@@ -1,15 +1,15 @@
-// Building blocks of the persistent, warp-specialised ("pipe") kernels: mbarrier
-// and bulk-async-copy (TMA engine, UBLKCP) wrappers, the ring bookkeeping, and the
-// producer-side planning of one tile (bounding box of all spline supports ->
-// geometry of the shared-memory box).
+// Building blocks of the persistent, warp-specialised ("pipe") kernels: mbarrier, TMA tile-copy and
+// bulk-reduction wrappers, the geometry of a staged box (planning from a bounding box of support
+// starts, boundary handling modes), the fix-up / fold passes for what the TMA unit cannot express,
+// and the host-side tensor-map encoder.
 //
-// One CTA per SM loops over tiles of TX x TY x TZ lattice points.  Warp 0 is the
-// producer: it streams the grid coordinates of upcoming tiles into a ring of
-// shared-memory buffers with 1-D bulk copies, reduces the bounding box of the
-// spline supports of a tile, and issues one bulk copy per row of the box of the
-// input volume (pull) / hands the geometry to the consumers (push).  All other
-// warps are consumers: they only ever wait on mbarriers, so the tap loop of tile
-// n overlaps with every memory phase of tiles n+1, n+2.
+// One CTA per SM (pull) or two (push) loop over tiles of TX x TY x TZ lattice points.  The last warp
+// is the producer: it streams the grid coordinates of upcoming tiles into a ring of shared-memory
+// buffers (one cp.async.bulk.tensor per tile), turns the bounding box the consumers reduced for a
+// tile into a plan (whole tile / z halves / z quarters), and requests one TMA box per x-plane of the
+// input volume (pull) or publishes the geometry of the accumulator box (push).  All other warps are
+// consumers: they only ever wait on mbarriers and counters, so the tap loop of tile n overlaps with
+// every memory phase of tiles n+1, n+2.
 #pragma once
 #include <cuda.h>
 #include "tile_common.cuh"

@@ -8,22 +8,21 @@
 //     - streams grid coordinates through a 4-deep TMA ring; turns the bounding box
 //       the consumers reduced two tiles ahead into a plan (whole tile / z halves /
 //       z quarters) and publishes the geometry of each (channel, part) item;
-//     - when the consumers have finished an item, flushes its box with ONE
-//       cp.reduce.async.bulk.tensor (float add) per x-plane: folds along x are
-//       applied to the plane coordinate, whatever lies outside the volume is
-//       clipped by the TMA unit (that IS the `zero` bound), and the copy of item n
-//       overlaps with the atomics of item n+1 (two boxes).
+//     - reopens the box as soon as every consumer warp has flushed and re-zeroed its planes
+//       (two CTAs per SM with one box each: the serial phases of one CTA hide behind the
+//       atomics of the other).
 //   consumer warps, per item (every step is claimed dynamically and closed by a
 //   counter, never by a barrier: a late warp delays nobody)
-//     Z. zero the box and the cell counters;
-//     H. count the sources per cell of (ORDER+1)^3 support starts, reduce max |value|;
+//     Z. load the values of the warp's rows (kept in registers), reduce max |value|;
+//     H. sum of |value| (quantised upwards) per cell of 4^3 support starts;
 //     S. rigorous bound on any accumulator (a target voxel receives from 2x2x2 cells)
-//        -> power-of-two fixed-point scale;
+//        -> power-of-two fixed-point scale (every warp recomputes it: no extra hand-shake);
 //     A. (ORDER+1)^3 integer atomics per source, z folded through a table for the
 //        mirror-type bounds; on the side, the box of tile q+2 is reduced;
 //     F. fold what sits outside the volume back inside (bounds the TMA clip / the
 //        x-plane coordinate / the z table do not already cover);
-//     C. fixed -> float in place, hand the box to the producer.
+//     C. per x-plane, by the warp that claims it: fixed -> float in place, ONE TMA float reduction into
+//        the volume, wait until the plane has been read, zero it for the next item.
 //
 // Replaces interpol/nd.py:147-213 (and iso1.py push) for the shapes that matter
 // for throughput; push_tile.cu / scatter.cu cover the rest.

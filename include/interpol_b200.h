@@ -176,6 +176,16 @@ IB200_API int ib200_resample_axis(const void *in, void *out, const void *coords,
                         int32_t order, int32_t bound, int32_t extrapolate,
                         int32_t all_nearest, int32_t all_linear, int32_t device, void *stream);
 
+/* Adjoint of ib200_resample_axis: out (outer, n_out, inner)[o, fold(start(coords[i]) + k), j] +=
+ * w_k(coords[i]) * in (outer, n_in, inner)[o, i, j]; `coords` has n_in values in voxel units of the
+ * OUTPUT axis; the callee zero-fills `out`.  One call per axis replaces the dense-grid construction +
+ * grid_push of interpol.restrict (interpol/restrict.py:86-120; plugin seam interpol/jitfields.py:106)
+ * and is the backward of a resize pass.  F32 / F64 only (IB200_ERR_DTYPE otherwise). */
+IB200_API int ib200_resample_axis_adjoint(const void *in, void *out, const void *coords, int32_t dtype,
+                                int64_t outer, int64_t n_in, int64_t n_out, int64_t inner,
+                                int32_t order, int32_t bound, int32_t extrapolate,
+                                int32_t all_nearest, int32_t all_linear, int32_t device, void *stream);
+
 /* Introspection */
 IB200_API int ib200_abi_version(void);
 IB200_API const char *ib200_error_string(int status);

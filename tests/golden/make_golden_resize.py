@@ -23,6 +23,14 @@ CASES.append(dict(shape=(7, 8, 6), factor=[2, 2, 2], anchor='c', order=[1, 3, 2]
 CASES.append(dict(shape=(7, 8, 6), factor=[0.7, 1.9, 1.2], anchor=['e', 'c', 'f'], order=4, bound='replicate', prefilter=True, extrapolate=2))
 
 
+# restrict (the adjoint): a subset of the same option space
+RCASES = []
+for shape, factor in (((23,), [2.3]), ((12, 15), [2, 1.5]), ((10, 9, 8), [1.5, 2, 1.25])):
+    for anchor in ('c', 'e', 'f', 'l'):
+        for order, bound in ((0, 'nearest'), (1, 'zero'), (2, 'dct2'), (3, 'dft'), (5, 'dct1')):
+            RCASES.append(dict(shape=shape, factor=factor, anchor=anchor, order=order, bound=bound, reduce_sum=(order % 2 == 0)))
+
+
 def make_input(i, shape):
     g = torch.Generator().manual_seed(5000 + i)
     return torch.randn([1, 2, *shape], generator=g, dtype=torch.float64)
@@ -38,5 +46,10 @@ if __name__ == '__main__':
         y = interpol.resize(x, factor=c['factor'], anchor=c['anchor'], interpolation=c['order'], bound=c['bound'],
                             prefilter=c['prefilter'], extrapolate=c['extrapolate'])
         out['case%d' % i] = y.numpy()
+    for i, c in enumerate(RCASES):
+        x = make_input(10000 + i, c['shape'])
+        y = interpol.restrict(x, factor=c['factor'], anchor=c['anchor'], interpolation=c['order'], bound=c['bound'],
+                              reduce_sum=c['reduce_sum'])
+        out['rcase%d' % i] = y.numpy()
     np.savez_compressed(os.path.join(HERE, 'resize.npz'), **out)
-    print('wrote', len(out), 'arrays for', len(CASES), 'cases')
+    print('wrote', len(out), 'arrays for', len(CASES), '+', len(RCASES), 'cases')

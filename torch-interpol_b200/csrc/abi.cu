@@ -248,30 +248,48 @@ int ib200_spline_coeff(void *data, int32_t dtype, int64_t outer, int64_t n, int6
     return launch_coeff(data, dtype, outer, n, inner, bound, order, (cudaStream_t)stream);
 }
 
-int ib200_resample_axis(const void *in, void *out, const void *coords, int32_t dtype, int64_t outer, int64_t n_in,
-                        int64_t n_out, int64_t inner, int32_t order, int32_t bound, int32_t extrapolate,
-                        int32_t all_nearest, int32_t all_linear, int32_t device, void *stream) {
+static int resample_common(int adjoint, const void *in, void *out, const void *coords, int32_t dtype, int64_t outer, int64_t n_src,
+                           int64_t n_dst, int64_t inner, int32_t order, int32_t bound, int32_t extrapolate,
+                           int32_t all_nearest, int32_t all_linear, int32_t device, void *stream) {
+    // forward: n_src = input extent, n_dst = number of coordinates (outputs); adjoint: n_src = number of
+    // coordinates (inputs), n_dst = output extent.  The coordinates always index the axis of extent `n_vol`.
+    const int64_t n_vol = adjoint ? n_dst : n_src, n_pts = adjoint ? n_src : n_dst;
     if (dtype_size(dtype) == 0) return IB200_ERR_DTYPE;
+    if (adjoint && dtype != IB200_F32 && dtype != IB200_F64) return IB200_ERR_DTYPE;
     if (bound < 0 || bound > 6) return IB200_ERR_BOUND;
     if (order < 0 || order > 7) return IB200_ERR_ORDER;
     if (extrapolate < 0 || extrapolate > 2) return IB200_ERR_EXTRAPOLATE;
-    if (outer < 0 || n_in < 1 || n_out < 0 || inner < 0) return IB200_ERR_SHAPE;
-    if (n_in > 0x7fffffffLL || n_out > 0x7fffffffLL || n_in * inner > 0x7fffffffLL) return IB200_ERR_TOO_LARGE;
-    if (outer * n_out * inner == 0) return IB200_OK;
-    if (!in || !out || !coords) return IB200_ERR_NULL;
+    if (outer < 0 || n_vol < 1 || n_pts < 0 || inner < 0) return IB200_ERR_SHAPE;
+    if (n_vol > 0x7fffffffLL || n_pts > 0x7fffffffLL || n_vol * inner > 0x7fffffffLL) return IB200_ERR_TOO_LARGE;
+    if (outer * n_dst * inner == 0) return IB200_OK;
+    if (!out || (outer * n_pts * inner != 0 && (!in || !coords))) return IB200_ERR_NULL;
     KParams kp;
     memset(&kp, 0, sizeof(kp));
     kp.dim = 1;
     kp.extrapolate = extrapolate;
     kp.round_nearest = all_nearest ? 1 : 0;
     kp.all_linear = all_linear ? 1 : 0;
-    kp.vol_n[0] = (int)n_in;
+    kp.vol_n[0] = (int)n_vol;
     const double thr = extrapolate == 2 ? 0.5 + 5e-2 : 5e-2;                  // nd.py:15-26
-    const double lo = round_to_dtype(-thr, dtype), hi = round_to_dtype((double)(n_in - 1) + thr, dtype);
+    const double lo = round_to_dtype(-thr, dtype), hi = round_to_dtype((double)(n_vol - 1) + thr, dtype);
     kp.thr_lo[0] = (float)lo; kp.thr_hi[0] = (float)hi; kp.thr_lo_d[0] = lo; kp.thr_hi_d[0] = hi;
     DeviceGuard guard(device);
     if (!guard.ok) return IB200_ERR_CUDA - (int)cudaErrorInvalidDevice;
-    return launch_resample(kp, dtype, in, out, coords, outer, n_in, n_out, inner, order, bound, extrapolate, (cudaStream_t)stream);
+    if (adjoint)
+        return launch_resample_adjoint(kp, dtype, in, out, coords, outer, n_src, n_dst, inner, order, bound, extrapolate, (cudaStream_t)stream);
+    return launch_resample(kp, dtype, in, out, coords, outer, n_src, n_dst, inner, order, bound, extrapolate, (cudaStream_t)stream);
+}
+
+int ib200_resample_axis(const void *in, void *out, const void *coords, int32_t dtype, int64_t outer, int64_t n_in,
+                        int64_t n_out, int64_t inner, int32_t order, int32_t bound, int32_t extrapolate,
+                        int32_t all_nearest, int32_t all_linear, int32_t device, void *stream) {
+    return resample_common(0, in, out, coords, dtype, outer, n_in, n_out, inner, order, bound, extrapolate, all_nearest, all_linear, device, stream);
+}
+
+int ib200_resample_axis_adjoint(const void *in, void *out, const void *coords, int32_t dtype, int64_t outer, int64_t n_in,
+                                int64_t n_out, int64_t inner, int32_t order, int32_t bound, int32_t extrapolate,
+                                int32_t all_nearest, int32_t all_linear, int32_t device, void *stream) {
+    return resample_common(1, in, out, coords, dtype, outer, n_in, n_out, inner, order, bound, extrapolate, all_nearest, all_linear, device, stream);
 }
 
 int ib200_abi_version(void) { return IB200_ABI_VERSION; }

@@ -134,6 +134,98 @@ static int launch_resample_t(const KParams &kp, const void *in, void *out, const
     return IB200_OK;
 }
 
+// ---- adjoint pass (restrict, backward of resize) ---------------------------------------------------
+// out[o, fold(start(c_i) + k), j] += w_k(c_i) * sign_k * in[o, i, j]: the transpose of the pass above,
+// i.e. one axis of grid_push on the tensor-product grid (interpol/restrict.py:86-120).  Global float
+// REDs, (order+1) per element and axis instead of (order+1)^dim per voxel; threads run along `inner`
+// (or along i when the axis is contiguous), so the REDs of a warp are coalesced.  `out` is zero-filled
+// by the launcher.  float32 / float64 storage.
+template <typename T>
+__global__ void __launch_bounds__(256)
+resample_adjoint_last_kernel(const __grid_constant__ KParams kp, const T *__restrict__ in, T *__restrict__ out,
+                             const T *__restrict__ coords, const i64 outer, const int n_in, const int n_out,
+                             const int order, const int bound, const int extrapolate) {
+    typedef typename Traits<T>::Real R;
+    const int i = blockIdx.x * 256 + threadIdx.x;      // index of the SOURCE sample (one coordinate each)
+    if (i >= n_in) return;
+    int idx[8]; R w[8];
+    resample_taps<R, T>(kp, coords, i, n_out, order, bound, extrapolate, idx, w);
+    for (i64 o = blockIdx.y; o < outer; o += gridDim.y) {
+        const R v = (R)Traits<T>::load(in + o * n_in + i);
+        T *line = out + o * n_out;
+        for (int k = 0; k <= order; ++k)
+            if (w[k] != R(0)) atomicAdd(line + idx[k], (T)(w[k] * v));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+resample_adjoint_inner_kernel(const __grid_constant__ KParams kp, const T *__restrict__ in, T *__restrict__ out,
+                              const T *__restrict__ coords, const i64 outer, const int n_in, const int n_out, const i64 inner,
+                              const int order, const int bound, const int extrapolate) {
+    typedef typename Traits<T>::Real R;
+    __shared__ int s_idx[kResIT][8];
+    __shared__ R s_w[kResIT][8];
+    const int i0 = blockIdx.x * kResIT, ni = min(kResIT, n_in - i0);
+    if ((int)threadIdx.x < ni) {
+        int idx[8]; R w[8];
+        resample_taps<R, T>(kp, coords, i0 + threadIdx.x, n_out, order, bound, extrapolate, idx, w);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_idx[threadIdx.x][k] = idx[k]; s_w[threadIdx.x][k] = w[k]; }
+    }
+    __syncthreads();
+    const i64 ncol = outer * inner;
+    for (i64 col = (i64)blockIdx.y * 256 + threadIdx.x; col < ncol; col += (i64)gridDim.y * 256) {
+        const i64 o = col / inner, j = col - o * inner;
+        const T *src = in + (o * n_in + i0) * inner + j;
+        T *base = out + o * n_out * inner + j;
+        for (int ii = 0; ii < ni; ++ii) {
+            const R v = (R)Traits<T>::load(src + (i64)ii * inner);
+            for (int k = 0; k <= order; ++k) {
+                const R wk = s_w[ii][k];
+                if (wk != R(0)) atomicAdd(base + (i64)s_idx[ii][k] * inner, (T)(wk * v));
+            }
+        }
+    }
+}
+
+template <typename T>
+static int launch_resample_adjoint_t(const KParams &kp, const void *in, void *out, const void *coords, i64 outer, i64 n_in,
+                                     i64 n_out, i64 inner, int order, int bound, int extrapolate, cudaStream_t stream) {
+    IB200_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)(outer * n_out * inner) * sizeof(T), stream));
+    if (outer * n_in * inner == 0) return IB200_OK;
+    if (inner == 1) {
+        const unsigned gx = (unsigned)((n_in + 255) / 256);
+        i64 gy = ((i64)kNumSMs * 16 + gx - 1) / gx;
+        if (gy > outer) gy = outer;
+        if (gy > 65535) gy = 65535;
+        resample_adjoint_last_kernel<T><<<dim3(gx, (unsigned)gy), 256, 0, stream>>>(kp, (const T *)in, (T *)out, (const T *)coords, outer,
+                                                                                    (int)n_in, (int)n_out, order, bound, extrapolate);
+        note_launch("resample_adjoint_last");
+    } else {
+        const unsigned gx = (unsigned)((n_in + kResIT - 1) / kResIT);
+        const i64 ncol = outer * inner;
+        i64 gy = ((i64)kNumSMs * 16 + gx - 1) / gx;
+        if (gy > (ncol + 255) / 256) gy = (ncol + 255) / 256;
+        if (gy > 65535) gy = 65535;
+        if (gy < 1) gy = 1;
+        resample_adjoint_inner_kernel<T><<<dim3(gx, (unsigned)gy), 256, 0, stream>>>(kp, (const T *)in, (T *)out, (const T *)coords, outer,
+                                                                                     (int)n_in, (int)n_out, inner, order, bound, extrapolate);
+        note_launch("resample_adjoint");
+    }
+    IB200_CUDA_CHECK(cudaGetLastError());
+    return IB200_OK;
+}
+
+int launch_resample_adjoint(const KParams &kp, int dtype, const void *in, void *out, const void *coords, i64 outer, i64 n_in,
+                            i64 n_out, i64 inner, int order, int bound, int extrapolate, cudaStream_t stream) {
+    switch (dtype) {
+    case IB200_F32: return launch_resample_adjoint_t<float>(kp, in, out, coords, outer, n_in, n_out, inner, order, bound, extrapolate, stream);
+    case IB200_F64: return launch_resample_adjoint_t<double>(kp, in, out, coords, outer, n_in, n_out, inner, order, bound, extrapolate, stream);
+    }
+    return IB200_ERR_DTYPE;
+}
+
 int launch_resample(const KParams &kp, int dtype, const void *in, void *out, const void *coords, i64 outer, i64 n_in, i64 n_out,
                     i64 inner, int order, int bound, int extrapolate, cudaStream_t stream) {
     switch (dtype) {

@@ -66,6 +66,8 @@ def lib():
         L.ib200_spline_coeff.argtypes = [vp, i32, i64, i64, i64, i32, i32, i32, vp]
         L.ib200_resample_axis.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, i32, i32, i32, vp]
         L.ib200_resample_axis.restype = ctypes.c_int
+        L.ib200_resample_axis_adjoint.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, i32, i32, i32, vp]
+        L.ib200_resample_axis_adjoint.restype = ctypes.c_int
         L.ib200_error_string.argtypes = [ctypes.c_int]
         L.ib200_error_string.restype = ctypes.c_char_p
         L.ib200_last_kernel.restype = ctypes.c_char_p

@@ -25,31 +25,6 @@ def _filter_axis_(x, bound: int, order: int, axis: int):
     _lib.check(st)
 
 
-def resample_axis(x, coords, axis: int, bound: int, order: int, extrapolate: int,
-                  all_nearest: bool, all_linear: bool):
-    """out[..., i, ...] = sum_k w_k(coords[i]) x[..., fold(start + k), ...] along `axis` of a dense
-    tensor: one separable pass of interpol.resize (interpol/resize.py:91-117)."""
-    _check(x)
-    x = x.contiguous()
-    coords = coords.to(device=x.device, dtype=x.dtype).contiguous()
-    n_in, n_out = x.shape[axis], coords.numel()
-    outer = 1
-    for s in x.shape[:axis]:
-        outer *= s
-    inner = 1
-    for s in x.shape[axis + 1:]:
-        inner *= s
-    out = torch.empty([*x.shape[:axis], n_out, *x.shape[axis + 1:]], dtype=x.dtype, device=x.device)
-    L = _lib.lib()
-    with torch.cuda.device(x.device):
-        st = L.ib200_resample_axis(_lib.ptr(x), _lib.ptr(out), _lib.ptr(coords), _lib.DTYPE_CODE[x.dtype],
-                                   outer, n_in, n_out, inner, int(order), int(bound), int(extrapolate),
-                                   int(bool(all_nearest)), int(bool(all_linear)), x.device.index,
-                                   _lib.stream_ptr(x.device))
-    _lib.check(st)
-    return out
-
-
 def _check(inp):
     _lib.require_cuda(inp)
     if inp.dtype not in _lib.DTYPE_CODE:

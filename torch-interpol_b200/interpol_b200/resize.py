@@ -5,7 +5,7 @@ The reference builds the dense sampling grid and calls `grid_pull`.  That grid i
 of one coordinate vector per axis and B-spline weights are separable, so the same result is obtained
 with one 1-D resampling pass per axis (`ib200_resample_axis`): no (B, *out, D) grid in HBM and
 3 (order+1) taps per voxel instead of (order+1)^3.  The dense-grid path is kept for what the separable
-kernel does not cover (integer label maps, inputs that require grad, > 3 spatial dims)."""
+kernels do not cover (integer label maps, 16-bit inputs that require grad, > 3 spatial dims)."""
 import torch
 
 from .api import grid_pull, _stage
@@ -84,8 +84,10 @@ def resize(image, factor=None, shape=None, anchor='c',
 def _separable_ok(image, nb_dim, kwargs):
     if not SEPARABLE:
         return False
-    if not torch.is_tensor(image) or not image.dtype.is_floating_point or image.requires_grad:
+    if not torch.is_tensor(image) or not image.dtype.is_floating_point:
         return False
+    if image.requires_grad and image.dtype not in (torch.float32, torch.float64):
+        return False        # the adjoint pass accumulates with float32 / float64 global atomics
     if nb_dim < 1 or nb_dim > 3 or image.dim() != nb_dim + 2 or image.numel() == 0:
         return False
     return set(kwargs) <= {'bound', 'extrapolate', 'interpolation', 'prefilter'} and \
@@ -93,7 +95,7 @@ def _separable_ok(image, nb_dim, kwargs):
 
 
 def _resize_separable(image, lin, nb_dim, interpolation=1, bound='nearest', extrapolate=True, prefilter=True):
-    from . import coeff as _coeff
+    from .separable import ResampleAxis
     from .api import spline_coeff_nd
     from .pushpull import pad_list_int
     from .autograd import _options
@@ -107,5 +109,5 @@ def _resize_separable(image, lin, nb_dim, interpolation=1, bound='nearest', extr
     # the axis that shrinks the most first: later passes stream less data
     axes = sorted(range(nb_dim), key=lambda d: lin[d].numel() / max(x.shape[2 + d], 1))
     for d in axes:
-        x = _coeff.resample_axis(x, lin[d], 2 + d, bnd[d], order[d], extrapolate, all_nearest, all_linear)
+        x = ResampleAxis.apply(x, lin[d], 2 + d, bnd[d], order[d], extrapolate, all_nearest, all_linear)
     return back(x)

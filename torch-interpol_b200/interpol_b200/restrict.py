@@ -1,9 +1,14 @@
-"""`restrict`: adjoint of `resize`, through `grid_push`
-(reference: interpol/restrict.py:9-122)."""
+"""`restrict`: adjoint of `resize` (reference: interpol/restrict.py:9-122; same arguments).
+
+The reference splats through `grid_push` on the dense tensor-product grid; here float32 / float64 images
+take one adjoint 1-D pass per axis (`ib200_resample_axis_adjoint`, see resize.py), everything else the
+dense grid + `grid_push`."""
 import torch
 
-from .api import grid_push
+from .api import grid_push, _stage
 from .utils import make_list, meshgrid_ij
+
+SEPARABLE = True     # False: always build the dense grid and call grid_push (A/B testing)
 
 __all__ = ['restrict']
 
@@ -59,8 +64,39 @@ def restrict(image, factor=None, shape=None, anchor='c',
     kwargs.setdefault('extrapolate', True)
     kwargs.setdefault('interpolation', interpolation)
     kwargs.setdefault('prefilter', False)
-    grid = torch.stack(meshgrid_ij(*lin), dim=-1)
-    resized = grid_push(image, grid, shape, **kwargs)
+    if _separable_ok(image, nb_dim, kwargs):
+        resized = _restrict_separable(image, lin, shape, nb_dim, **kwargs)
+    else:
+        grid = torch.stack(meshgrid_ij(*lin), dim=-1)
+        resized = grid_push(image, grid, shape, **kwargs)
     if not reduce_sum:
-        resized /= fullscale
+        resized = resized / fullscale if resized.requires_grad else resized.div_(fullscale)
     return resized
+
+
+def _separable_ok(image, nb_dim, kwargs):
+    if not SEPARABLE or not torch.is_tensor(image) or image.dtype not in (torch.float32, torch.float64):
+        return False
+    if nb_dim < 1 or nb_dim > 3 or image.dim() != nb_dim + 2 or image.numel() == 0:
+        return False
+    return set(kwargs) <= {'bound', 'extrapolate', 'interpolation', 'prefilter'} and \
+        (image.is_cuda or torch.cuda.is_available())
+
+
+def _restrict_separable(image, lin, shape, nb_dim, interpolation=1, bound='nearest', extrapolate=True, prefilter=False):
+    from .api import spline_coeff_nd
+    from .autograd import _options
+    from .pushpull import pad_list_int
+    from .separable import ResampleAxisAdjoint
+    bnd, order, extrapolate = _options(interpolation, bound, extrapolate)
+    order, bnd = pad_list_int(order, nb_dim), pad_list_int(bnd, nb_dim)
+    (x,), back = _stage(image)
+    all_nearest = all(o == 0 for o in order)
+    all_linear = all(o == 1 for o in order)
+    # the axis that shrinks the most first: later passes stream less data
+    axes = sorted(range(nb_dim), key=lambda d: shape[d] / max(x.shape[2 + d], 1))
+    for d in axes:
+        x = ResampleAxisAdjoint.apply(x, lin[d], 2 + d, int(shape[d]), bnd[d], order[d], extrapolate, all_nearest, all_linear)
+    if prefilter:
+        x = spline_coeff_nd(x, interpolation=interpolation, bound=bound, dim=nb_dim, inplace=not x.requires_grad)
+    return back(x)

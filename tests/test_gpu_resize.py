@@ -44,6 +44,9 @@ def test_restrict_vs_reference_golden():
         x = mg.make_input(10000 + i, c['shape'])
         want = gold['rcase%d' % i]
         for dt, tol in ((torch.float64, 1e-10), (torch.float32, 1e-5)):
+            if dt == torch.float32 and c['order'] == 0:
+                continue        # nearest at coordinates that are exact halves in float64 (e.g. i * 2/3 - 1/6): the
+                                # float32 lattice lands on either side; float64 is compared above
             got = ib.restrict(x.to(dt).cuda(), factor=c['factor'], anchor=c['anchor'], interpolation=c['order'],
                               bound=c['bound'], reduce_sum=c['reduce_sum'])
             assert ib.last_kernel().startswith('resample_adjoint'), ib.last_kernel()

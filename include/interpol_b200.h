@@ -164,6 +164,15 @@ IB200_API int ib200_spline_coeff(void *data, int32_t dtype, int64_t outer, int64
                        int64_t inner, int32_t bound, int32_t order,
                        int32_t device, void *stream);
 
+/* out (B, C, *pts_shape) int32 = label map `vol` (B, C, *vol_shape) int32 resampled at `grid`: for every
+ * point the label whose soft mask (vol == label) interpolates to the largest value (> 0, ties to the
+ * smallest label, 0 when nothing is in bounds).  One pass replaces the loop over `input.unique()` of
+ * interpol.grid_pull (interpol/api.py:194-205: one full pull per label).  Orders 0 / 1 per axis
+ * (IB200_ERR_ORDER otherwise: higher orders prefilter the masks); p->dtype is the dtype of the GRID
+ * (F32 / F64), vol_stride counts int32 elements. */
+IB200_API int ib200_pull_labels(const ib200_problem *p, const void *vol, const void *grid,
+                      void *out, void *stream);
+
 /* Separable resampling along one axis of a dense tensor viewed as (outer, n_in, inner):
  * out (outer, n_out, inner)[o, i, j] = sum_k w_k(coords[i]) * in[o, fold(start + k), j].
  * One call per axis replaces the dense-grid construction + grid_pull of interpol.resize

@@ -393,3 +393,40 @@ def test_reference_side_by_side():
     want = ref.spline_coeff_nd(vol.double(), interpolation=3, bound='dct2', dim=3)
     got = ib.spline_coeff_nd(vol.cuda(), interpolation=3, bound='dct2', dim=3)
     assert rel_err(to_np(got), want.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize('dim', [1, 2, 3])
+def test_label_pull_fused_matches_label_loop(dim):
+    """integer label maps: the one-pass kernel (ib200_pull_labels) returns what the reference's loop over
+    `input.unique()` (api.py:194-205, run here through grid_pull of the soft masks) returns."""
+    import interpol_b200 as ib
+    import interpol_b200.api as api
+    gen = torch.Generator().manual_seed(40 + dim)
+    shape = {1: (200,), 2: (40, 36), 3: (20, 18, 22)}[dim]
+    for dtype in (torch.int64, torch.uint8, torch.int32):
+        lab = torch.randint(0, 7, [2, 2, *shape], generator=gen).to(dtype)
+        if dtype != torch.uint8:
+            lab = lab * 37 - 60            # negative and sparse label values
+        grid = smooth_grid(shape, gen, amp=3.0, batch=2).contiguous()
+        for order, bound, ex in ((1, 'dct2', True), (0, 'zero', False), ([1, 0, 1][:dim], 'dft', True), (1, 'dst2', 2), (1, 'replicate', False)):
+            a = ib.grid_pull(lab.cuda(), grid.cuda(), interpolation=order, bound=bound, extrapolate=ex)
+            assert ib.last_kernel() == 'pull_labels', ib.last_kernel()
+            api.LABELS_FUSED = False
+            try:
+                b = ib.grid_pull(lab.cuda(), grid.cuda(), interpolation=order, bound=bound, extrapolate=ex)
+            finally:
+                api.LABELS_FUSED = True
+            assert ib.last_kernel() != 'pull_labels'
+            assert a.dtype == b.dtype == dtype and a.shape == b.shape
+            # identical except where two masks tie to rounding (both kernels sum the same terms in the same order)
+            assert (a != b).float().mean().item() <= 1e-4, (dim, dtype, order, bound, ex)
+    # exact ties (up-sampling by 2 with linear weights: 0.5 / 0.5): the smallest label wins in both
+    lab = torch.randint(0, 5, [1, 1, *shape], generator=gen).cuda()
+    ident = ib.identity_grid(shape, device='cuda')[None] * 0.5
+    a = ib.grid_pull(lab, ident, interpolation=1, bound='replicate', extrapolate=True)
+    api.LABELS_FUSED = False
+    try:
+        b = ib.grid_pull(lab, ident, interpolation=1, bound='replicate', extrapolate=True)
+    finally:
+        api.LABELS_FUSED = True
+    assert torch.equal(a, b)

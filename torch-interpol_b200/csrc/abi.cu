@@ -248,6 +248,27 @@ int ib200_spline_coeff(void *data, int32_t dtype, int64_t outer, int64_t n, int6
     return launch_coeff(data, dtype, outer, n, inner, bound, order, (cudaStream_t)stream);
 }
 
+} // extern "C" (reopened below)
+
+namespace ib200 {
+static int run_labels(const ib200_problem *p, const void *vol, const void *grid, void *out, void *stream) {
+    KParams kp;
+    int st = build_params(p, NEED_VOL_IN, kp);
+    if (st != IB200_OK) return st;
+    if (kp.batch * kp.pts_total == 0 || kp.channels == 0) return IB200_OK;
+    if (!vol || !grid || !out) return IB200_ERR_NULL;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return IB200_ERR_CUDA - (int)cudaErrorInvalidDevice;
+    return launch_pull_labels(kp, p->dtype, vol, grid, out, (cudaStream_t)stream);
+}
+}  // namespace ib200
+
+extern "C" {
+
+int ib200_pull_labels(const ib200_problem *p, const void *vol, const void *grid, void *out, void *stream) {
+    return run_labels(p, vol, grid, out, stream);
+}
+
 static int resample_common(int adjoint, const void *in, void *out, const void *coords, int32_t dtype, int64_t outer, int64_t n_src,
                            int64_t n_dst, int64_t inner, int32_t order, int32_t bound, int32_t extrapolate,
                            int32_t all_nearest, int32_t all_linear, int32_t device, void *stream) {

@@ -136,6 +136,25 @@ def _postproc(out, shape_info, mode):
     return out.reshape([*batch, *channel, *spatial, *feat])
 
 
+LABELS_FUSED = True      # False: always loop over the labels like the reference (A/B testing)
+
+
+def _labels_fused_ok(input, grid, interpolation):
+    """The fused label kernel covers orders 0 / 1 (no prefilter involved), float32 / float64 grids, and
+    labels that fit in int32."""
+    if not LABELS_FUSED or grid.dtype not in (torch.float32, torch.float64) or input.numel() == 0:
+        return False
+    from .autograd import inter_to_nitorch, make_list
+    if any(o > 1 for o in inter_to_nitorch(make_list(interpolation), as_type='int')):
+        return False
+    if input.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32):
+        return True
+    if input.dtype == torch.int64:
+        lo, hi = input.amin().item(), input.amax().item()
+        return -2 ** 31 <= lo and hi < 2 ** 31
+    return False
+
+
 # --------------------------------------------------------------------------
 # public functions
 # --------------------------------------------------------------------------
@@ -158,7 +177,13 @@ def grid_pull(input, grid, interpolation='linear', bound='zero',
     batch, channel = input.shape[:2]
     dim = grid.shape[-1]
 
-    if not input.dtype.is_floating_point:
+    if not input.dtype.is_floating_point and _labels_fused_ok(input, grid, interpolation):
+        # one pass: every point looks for the arg-max among the labels of its own (order+1)^dim nodes
+        from .autograd import _options
+        from . import pushpull as _pp
+        bnd, order, extr = _options(interpolation, bound, extrapolate)
+        out = _pp.grid_pull_labels(input.to(torch.int32), grid, bnd, order, extr).to(input.dtype)
+    elif not input.dtype.is_floating_point:
         out = input.new_zeros([batch, channel, *grid.shape[1:-1]])
         pmax = grid.new_zeros([batch, channel, *grid.shape[1:-1]])
         for label in input.unique():

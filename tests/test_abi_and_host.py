@@ -236,3 +236,32 @@ def test_pinned_result_pool_reuses_released_buffers(monkeypatch):
     d = api._pinned_empty([2, 5], torch.float64)
     assert d.data_ptr() == pa and d.shape == (2, 5) and d.dtype == torch.float64
     assert len(api._POOL) == 3
+
+
+def test_label_and_separable_dispatch_rules():
+    """host-side routing (no CUDA needed): which inputs take the one-pass label kernel / the separable
+    resize and restrict passes, and which fall back to the reference's own formulation."""
+    import importlib
+    import torch
+    import interpol_b200.api as api
+    rz = importlib.import_module('interpol_b200.resize')
+    rs = importlib.import_module('interpol_b200.restrict')
+    g32 = torch.zeros(1, 4, 4, 2)
+    lab = torch.randint(0, 5, [1, 1, 4, 4])
+    assert api._labels_fused_ok(lab, g32, 1) and api._labels_fused_ok(lab.to(torch.uint8), g32, [0, 1])
+    assert not api._labels_fused_ok(lab, g32, 3)                      # higher orders prefilter the masks
+    assert not api._labels_fused_ok(lab, g32.half(), 1)               # 16-bit grids: label loop
+    assert not api._labels_fused_ok(lab + 2 ** 40, g32, 1)            # labels must fit in int32
+    x = torch.zeros(1, 1, 8, 8)
+    ok_cuda = torch.cuda.is_available()
+    assert rz._separable_ok(x, 2, {'bound': 'dct2'}) == ok_cuda
+    assert not rz._separable_ok(x, 1, {})                             # spatial dims must be the trailing ones exactly
+    assert not rz._separable_ok(x.long(), 2, {})                      # label maps
+    assert not rz._separable_ok(x.half().requires_grad_(), 2, {})     # 16-bit adjoint not available
+    assert not rz._separable_ok(x, 2, {'unknown_option': 1})
+    assert rs._separable_ok(x, 2, {}) == ok_cuda and not rs._separable_ok(x.half(), 2, {})
+    rz.SEPARABLE = False
+    try:
+        assert not rz._separable_ok(x, 2, {})
+    finally:
+        rz.SEPARABLE = True

@@ -32,17 +32,23 @@ BOUND_CODE = 3
 BYTES_PER_VOXEL = 20   # fp32, D=3, C=1: 12 (grid) + 4 (read) + 4 (write); SURVEY 8(d)
 
 
-def make_workload(size, device, seed=1234):
-    """N(0,1) volume; grid = identity + randn(1,3,8,8,8)*3 voxels
-    up-sampled tri-linearly (|disp| <~ 10 voxels, ~5 % of samples out of bounds)."""
+def make_workload(size, device, seed=1234, channels=1, batch=1, dtype=torch.float32, incoherent=False, dim=3):
+    """N(0,1) volume; grid = identity + randn(B,D,8,..,8)*3 voxels
+    up-sampled (tri)linearly (|disp| <~ 10 voxels, ~5 % of samples out of bounds);
+    `incoherent` adds randn * 20 voxels on top (scatter stress, cfg 4).  16-bit
+    types are generated in float32 and rounded."""
     g = torch.Generator(device='cpu').manual_seed(seed)
-    vol = torch.randn([1, 1, size, size, size], generator=g).to(device)
-    coarse = (torch.randn([1, 3, 8, 8, 8], generator=g) * 3.0).to(device)
-    disp = torch.nn.functional.interpolate(coarse, size=[size] * 3, mode='trilinear', align_corners=True)
+    vol = torch.randn([batch, channels] + [size] * dim, generator=g).to(device)
+    coarse = (torch.randn([batch, dim] + [8] * dim, generator=g) * 3.0).to(device)
+    mode = {2: 'bilinear', 3: 'trilinear'}[dim]
+    disp = torch.nn.functional.interpolate(coarse, size=[size] * dim, mode=mode, align_corners=True)
     ar = torch.arange(size, dtype=torch.float32, device=device)
-    ident = torch.stack(torch.meshgrid(ar, ar, ar, indexing='ij'), dim=-1)
-    grid = (disp.permute(0, 2, 3, 4, 1) + ident).contiguous()
-    return vol, grid
+    ident = torch.stack(torch.meshgrid(*([ar] * dim), indexing='ij'), dim=-1)
+    grid = disp.movedim(1, -1) + ident
+    if incoherent:
+        gd = torch.Generator(device=device).manual_seed(seed + 1)
+        grid = grid + torch.randn(grid.shape, generator=gd, device=device) * 20.0
+    return vol.to(dtype), grid.contiguous().to(dtype)
 
 
 class ClockSampler(threading.Thread):

@@ -1,0 +1,259 @@
+"""GPU parity of the TILED kernels (the default path for dense 3-D problems with >= 32768 lattice points)
+against the float64 oracle: pull / grad / push / count x orders 1-7 x {float32, float16} x mixed per-dim
+bounds x extrapolate 0 / 1 / 2, on shapes above the dispatch threshold with partial tiles, asserting that
+the tile (or pipe) kernel -- not the generic one-thread-per-point kernel -- produced the result.
+Full-size BASELINE configs 3, 4 and 5 (one shard) against the OpenMP oracle.
+
+Reference: interpol/nd.py:81-288 (pull / push / grad), interpol/iso1.py (order 1)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from test_gpu_ops import smooth_grid, to_np
+
+pytestmark = pytest.mark.gpu
+
+SHAPE = (40, 44, 36)          # 63 360 points: above the 32 768 threshold, partial tiles along x, y and z
+VSHAPE = (36, 50, 41)         # the volume has its own (odd) shape
+
+
+def _case(order, seed, dtype=torch.float32, B=2, C=2, amp=3.0):
+    gen = torch.Generator().manual_seed(seed)
+    vol = torch.randn([B, C, *VSHAPE], generator=gen)
+    img = torch.randn([B, C, *SHAPE], generator=gen)
+    grid = smooth_grid(SHAPE, gen, amp=amp, batch=B)
+    scale = torch.tensor([VSHAPE[d] / SHAPE[d] for d in range(3)])
+    grid = (grid * scale - 1.25).contiguous()                 # leaves the field of view on the low side
+    if dtype != torch.float32:
+        vol, img, grid = vol.to(dtype), img.to(dtype), grid.to(dtype)
+    return vol, img, grid
+
+
+def _tiled(name, op):
+    return name.startswith(op + '_tile3d') or name.startswith(op + '_pipe3d') or name.startswith(op + '_tap')
+
+
+@pytest.mark.parametrize('extrapolate', [1, 0, 2])
+@pytest.mark.parametrize('order', [1, 2, 3, 4, 5, 6, 7])
+def test_tile_kernels_vs_oracle_f32(order, extrapolate):
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    vol, img, grid = _case(order, 500 + 10 * order + extrapolate)
+    grid = _off_threshold(grid, VSHAPE)
+    bound = [(order + extrapolate) % 7, (order + 2) % 7, (order + 4 + extrapolate) % 7]
+    o = [order]
+    v64, i64, g64 = vol.double().numpy(), img.double().numpy(), grid.double().numpy()
+    tol = 1e-5
+    got = pp.grid_pull(vol.cuda(), grid.cuda(), bound, o, extrapolate)
+    assert _tiled(ib.last_kernel(), 'pull'), ib.last_kernel()
+    assert rel_err(to_np(got), oracle.grid_pull(v64, g64, bound, o, extrapolate)) <= tol
+    got = pp.grid_grad(vol.cuda(), grid.cuda(), bound, o, extrapolate)
+    assert _tiled(ib.last_kernel(), 'grad'), ib.last_kernel()
+    assert rel_err(to_np(got), oracle.grid_grad(v64, g64, bound, o, extrapolate)) <= tol
+    got = pp.grid_push(img.cuda(), grid.cuda(), list(VSHAPE), bound, o, extrapolate)
+    assert _tiled(ib.last_kernel(), 'push'), ib.last_kernel()
+    assert rel_err(to_np(got), oracle.grid_push(i64, g64, VSHAPE, bound, o, extrapolate)) <= tol
+    got = pp.grid_count(grid.cuda(), list(VSHAPE), bound, o, extrapolate)
+    assert _tiled(ib.last_kernel(), 'count'), ib.last_kernel()
+    assert rel_err(to_np(got), oracle.grid_count(g64, VSHAPE, bound, o, extrapolate)) <= tol
+
+
+def _off_threshold(grid, vshape):
+    """extrapolate 0 / 2 keep a point iff -t < g < n - 1 + t with the thresholds rounded to the GRID's dtype
+    (nd.py:11-27): a float32 coordinate that equals the rounded threshold is masked in float32 and kept in
+    float64.  Move such points (one in ~1e6) so that the float64 oracle answers the same question."""
+    grid = grid.clone()
+    for d in range(3):
+        for t in (0.05, 0.55):
+            for thr in (-t, vshape[d] - 1 + t):
+                near = (grid[..., d] - thr).abs() < 1e-4
+                grid[..., d][near] += 3e-4
+    return grid
+
+
+def _splat_tol(fn32, fn64):
+    """Tolerance for push / count: 1e-5, or the reference's own float32 noise floor where that is larger --
+    bounds that pile everything outside the field of view onto the border voxels (replicate) accumulate
+    hundreds of float32 partial sums per voxel and the float32 reference itself is 3-4e-5 away from float64."""
+    return max(1e-5, 1.5 * rel_err(np.asarray(fn32, dtype=np.float64), fn64))
+
+
+@pytest.mark.parametrize('bound', range(7))
+@pytest.mark.parametrize('order', [1, 3, 5])
+def test_tile_kernels_every_bound_f32(order, bound):
+    """isotropic bound, all seven, deformation reaching well outside the volume on both sides"""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    vol, img, grid = _case(order, 900 + 10 * order + bound, amp=6.0)
+    grid = _off_threshold((grid * 1.2 - 3.0).contiguous(), VSHAPE)
+    b, o = [bound], [order]
+    v64, i64, g64 = vol.double().numpy(), img.double().numpy(), grid.double().numpy()
+    for ex in (1, 0):
+        got = pp.grid_pull(vol.cuda(), grid.cuda(), b, o, ex)
+        assert _tiled(ib.last_kernel(), 'pull'), ib.last_kernel()
+        assert rel_err(to_np(got), oracle.grid_pull(v64, g64, b, o, ex)) <= 1e-5
+        got = pp.grid_grad(vol.cuda(), grid.cuda(), b, o, ex)
+        assert rel_err(to_np(got), oracle.grid_grad(v64, g64, b, o, ex)) <= 1e-5
+        got = pp.grid_push(img.cuda(), grid.cuda(), list(VSHAPE), b, o, ex)
+        assert _tiled(ib.last_kernel(), 'push'), ib.last_kernel()
+        want = oracle.grid_push(i64, g64, VSHAPE, b, o, ex)
+        assert rel_err(to_np(got), want) <= _splat_tol(oracle.grid_push(img.numpy(), grid.numpy(), VSHAPE, b, o, ex), want)
+        got = pp.grid_count(grid.cuda(), list(VSHAPE), b, o, ex)
+        want = oracle.grid_count(g64, VSHAPE, b, o, ex)
+        assert rel_err(to_np(got), want) <= _splat_tol(oracle.grid_count(grid.numpy(), VSHAPE, b, o, ex), want)
+
+
+@pytest.mark.parametrize('extrapolate', [1, 0])
+@pytest.mark.parametrize('order', [1, 2, 3, 4, 5, 6, 7])
+def test_tile_kernels_vs_oracle_f16(order, extrapolate):
+    """float16 storage (volume, image and grid), float32 arithmetic: 1e-2 against the float64 oracle on the
+    float16-rounded inputs (north-star tolerance; SURVEY 8d parity gates)"""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    vol, img, grid = _case(order, 700 + 10 * order + extrapolate, dtype=torch.float16)
+    bound = [(order + 1) % 7, 6, (order + 3) % 7]
+    o = [order]
+    v64, i64, g64 = vol.double().numpy(), img.double().numpy(), grid.double().numpy()
+    got = pp.grid_pull(vol.cuda(), grid.cuda(), bound, o, extrapolate)
+    assert got.dtype == torch.float16
+    assert _tiled(ib.last_kernel(), 'pull'), ib.last_kernel()
+    assert rel_err(to_np(got), oracle.grid_pull(v64, g64, bound, o, extrapolate)) <= 1e-2
+    got = pp.grid_grad(vol.cuda(), grid.cuda(), bound, o, extrapolate)
+    assert _tiled(ib.last_kernel(), 'grad'), ib.last_kernel()
+    assert rel_err(to_np(got), oracle.grid_grad(v64, g64, bound, o, extrapolate)) <= 1e-2
+    got = pp.grid_push(img.cuda(), grid.cuda(), list(VSHAPE), bound, o, extrapolate)
+    assert got.dtype == torch.float16
+    assert rel_err(to_np(got), oracle.grid_push(i64, g64, VSHAPE, bound, o, extrapolate)) <= 1e-2
+    got = pp.grid_count(grid.cuda(), list(VSHAPE), bound, o, extrapolate)
+    assert rel_err(to_np(got), oracle.grid_count(g64, VSHAPE, bound, o, extrapolate)) <= 1e-2
+
+
+def test_push_tile_nonfinite_values_propagate():
+    """NaN / Inf in the pushed image must reach the touched voxels (as in the reference's
+    scatter_add_ and in the generic kernel), not turn into finite garbage."""
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    vol, img, grid = _case(3, 4242, B=1, C=1)
+    img = img.clone()
+    img[0, 0, 10, 12, 9] = float('nan')
+    img[0, 0, 30, 5, 20] = float('inf')
+    img[0, 0, 31, 40, 3] = -float('inf')
+    for order in (1, 3):
+        got = pp.grid_push(img.cuda(), grid.cuda(), list(VSHAPE), [3], [order], 1)
+        assert _tiled(ib.last_kernel(), 'push'), ib.last_kernel()
+        old = pp.flags
+        pp.flags = 1            # NO_TILES: the generic scatter kernel
+        try:
+            want = pp.grid_push(img.cuda(), grid.cuda(), list(VSHAPE), [3], [order], 1)
+        finally:
+            pp.flags = old
+        assert torch.equal(torch.isnan(got), torch.isnan(want))
+        assert torch.equal(torch.isposinf(got), torch.isposinf(want))
+        assert torch.equal(torch.isneginf(got), torch.isneginf(want))
+        ok = torch.isfinite(want)
+        assert rel_err(to_np(got[ok]), to_np(want[ok])) <= 1e-5
+
+
+@pytest.mark.parametrize('ratio', [1e3, 1e5, 1e8])
+def test_push_tile_high_dynamic_range(ratio):
+    """one large outlier among unit-scale values must not wipe out the precision of its
+    neighbours (float64 oracle, error measured on the voxels the outlier does not touch, relative to THEIR
+    magnitude)."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    vol, img, grid = _case(3, 777, B=1, C=1)
+    img = img.clone()
+    img[0, 0, 20, 22, 18] = ratio
+    got = pp.grid_push(img.cuda(), grid.cuda(), list(VSHAPE), [3], [3], 1)
+    assert _tiled(ib.last_kernel(), 'push'), ib.last_kernel()
+    want = oracle.grid_push(img.double().numpy(), grid.double().numpy(), VSHAPE, [3], [3], 1)
+    base = img.clone(); base[0, 0, 20, 22, 18] = 0
+    want0 = oracle.grid_push(base.double().numpy(), grid.double().numpy(), VSHAPE, [3], [3], 1)
+    far = np.abs(want - want0) == 0                  # voxels the outlier does not reach
+    assert far.sum() > 0.9 * far.size
+    assert rel_err(to_np(got)[far], want[far]) <= 1e-5
+    assert rel_err(to_np(got), want) <= 1e-5
+
+
+# ------------------------------------------------ BASELINE configs at full size --
+
+def _bench():
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    return bench
+
+
+def test_cfg3_full_size_vs_oracle():
+    """BASELINE config 3: 256^3 fp32, 4 channels, cubic, dct2: spline_coeff_nd -> grid_pull, grid_grad."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    bench = _bench()
+    vol, grid = bench.make_workload(256, 'cuda', channels=4)
+    coeff = ib.spline_coeff_nd(vol, interpolation=3, bound='dct2', dim=3)
+    v64, g64 = to_np(vol), to_np(grid)
+    c64 = oracle.spline_coeff_nd(v64, [3], [3], 3)
+    assert rel_err(to_np(coeff), c64) <= 1e-5
+    del v64
+    pull = pp.grid_pull(coeff, grid, [3], [3], 1)
+    k_pull = ib.last_kernel()
+    grad = pp.grid_grad(coeff, grid, [3], [3], 1)
+    k_grad = ib.last_kernel()
+    assert _tiled(k_pull, 'pull') and _tiled(k_grad, 'grad'), (k_pull, k_grad)
+    cc = to_np(coeff)
+    assert rel_err(to_np(pull), oracle.grid_pull(cc, g64, [3], [3], 1)) <= 1e-5
+    assert rel_err(to_np(grad), oracle.grid_grad(cc, g64, [3], [3], 1)) <= 1e-5
+
+
+@pytest.mark.parametrize('kind', ['smooth', 'incoherent'])
+def test_cfg4_full_size_vs_oracle(kind):
+    """BASELINE config 4: 256^3 fp16 (volume and grid), order 5, dft, grid_push + grid_count; smooth
+    deformation and identity + randn * 20 (scatter stress).  1e-2 vs the float64 oracle on the rounded inputs."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    bench = _bench()
+    vol, grid = bench.make_workload(256, 'cuda', dtype=torch.float16, incoherent=(kind == 'incoherent'))
+    push = pp.grid_push(vol, grid, [256] * 3, [6], [5], 1)
+    count = pp.grid_count(grid, [256] * 3, [6], [5], 1)
+    v64, g64 = to_np(vol), to_np(grid)
+    assert rel_err(to_np(push), oracle.grid_push(v64, g64, [256] * 3, [6], [5], 1, nthreads=8)) <= 1e-2
+    assert rel_err(to_np(count), oracle.grid_count(g64, [256] * 3, [6], [5], 1, nthreads=8)) <= 1e-2
+
+
+def test_cfg5_shard_vs_oracle():
+    """BASELINE config 5, one GPU's shard: batch 8 x 192^3 fp32, cubic, bounds (dct2, dft, zero), pull + push."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    bench = _bench()
+    vol, grid = bench.make_workload(192, 'cuda', batch=8)
+    bound = [3, 6, 0]
+    pull = pp.grid_pull(vol, grid, bound, [3], 1)
+    assert _tiled(ib.last_kernel(), 'pull'), ib.last_kernel()
+    push = pp.grid_push(pull, grid, [192] * 3, bound, [3], 1)
+    assert _tiled(ib.last_kernel(), 'push'), ib.last_kernel()
+    v64, g64 = to_np(vol), to_np(grid)
+    assert rel_err(to_np(pull), oracle.grid_pull(v64, g64, bound, [3], 1)) <= 1e-5
+    assert rel_err(to_np(push), oracle.grid_push(to_np(pull), g64, [192] * 3, bound, [3], 1, nthreads=8)) <= 1e-5
+
+
+def test_headline_256_vs_oracle():
+    """The north-star configuration itself (256^3 fp32 cubic dct2, C = 1) against the OpenMP oracle."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    bench = _bench()
+    vol, grid = bench.make_workload(256, 'cuda')
+    pull = pp.grid_pull(vol, grid, [3], [3], 1)
+    k = ib.last_kernel()
+    push = pp.grid_push(pull, grid, [256] * 3, [3], [3], 1)
+    v64, g64 = to_np(vol), to_np(grid)
+    assert rel_err(to_np(pull), oracle.grid_pull(v64, g64, [3], [3], 1)) <= 1e-5, k
+    assert rel_err(to_np(push), oracle.grid_push(to_np(pull), g64, [256] * 3, [3], [3], 1, nthreads=8)) <= 1e-5

@@ -17,7 +17,7 @@ from .autograd import (GridPull, GridPush, GridCount, GridGrad,
                        SplineCoeff, SplineCoeffND)
 
 __all__ = [
-    'pull', 'push', 'count',
+    'pull', 'push', 'count', 'stage_scope',
     'grid_pull', 'grid_push', 'grid_count', 'grid_grad',
     'spline_coeff', 'spline_coeff_nd',
     'identity_grid', 'add_identity_grid', 'add_identity_grid_', 'affine_grid',
@@ -30,31 +30,111 @@ __all__ = [
 
 # Page-locking a fresh 64 MB buffer costs ~11 ms (cudaHostAlloc; measured, profiles/xfer_rates.py) -- ten
 # times the copy it serves -- so result buffers come from a small pool and are handed out again once the
-# caller has dropped every tensor that views them (storage use count back to the pool's own reference).
-_POOL, _POOL_LOCK, _POOL_MAX_BYTES = [], threading.Lock(), 4 << 30
+# caller has dropped every tensor that views them (storage use count back to the pool's own references).
+# Buffers are reused for results of exactly the same byte size only, so a result never views a storage
+# larger than itself (torch.save / pickling serialise whole storages).  The pool is capped
+# (IB200_PINNED_POOL_MB, default 1024; 0 disables it) and switches itself off if torch's storage use
+# count does not behave as the reuse test assumes.
+import os as _os
+
+_POOL, _POOL_LOCK = [], threading.Lock()
+_POOL_MAX_BYTES = int(_os.environ.get('IB200_PINNED_POOL_MB', '1024')) << 20
+_POOL_STATE = {'checked': False, 'ok': False, 'idle': 0}
+
+
+def _use_count_fn():
+    """torch._C._storage_Use_Count, after a self-test of the semantics the pool relies on: a view adds one
+    reference, dropping it gives the reference back."""
+    st = _POOL_STATE
+    if not st['checked']:
+        st['checked'] = True
+        fn = getattr(torch._C, '_storage_Use_Count', None)
+        try:
+            probe = torch.empty(16, dtype=torch.uint8)
+            idle = fn(probe.untyped_storage()._cdata)
+            view = probe[:8]
+            held = fn(probe.untyped_storage()._cdata)
+            del view
+            st['ok'] = held == idle + 1 and fn(probe.untyped_storage()._cdata) == idle
+            st['idle'] = idle
+        except Exception:
+            st['ok'] = False
+    return getattr(torch._C, '_storage_Use_Count') if st['ok'] else None
 
 
 def _pinned_empty(shape, dtype):
-    use_count = getattr(torch._C, '_storage_Use_Count', None)
     nbytes = 1
     for n in shape:
         nbytes *= int(n)
     nbytes *= torch.empty(0, dtype=dtype).element_size()
-    if use_count is None or nbytes == 0:
+    use_count = _use_count_fn() if _POOL_MAX_BYTES > 0 else None
+    if use_count is None or nbytes == 0 or nbytes > _POOL_MAX_BYTES:
         return torch.empty(shape, dtype=dtype, pin_memory=True)
     with _POOL_LOCK:
         best = None
         for buf in _POOL:
-            if buf.numel() >= nbytes and (best is None or buf.numel() < best.numel()) \
-                    and use_count(buf.untyped_storage()._cdata) <= 2:
+            if buf.numel() == nbytes and use_count(buf.untyped_storage()._cdata) <= _POOL_STATE['idle']:
                 best = buf
+                break
         if best is None:
             total = sum(b.numel() for b in _POOL)
             while _POOL and total + nbytes > _POOL_MAX_BYTES:
                 total -= _POOL.pop(0).numel()
             best = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
             _POOL.append(best)
-        return best[:nbytes].view(dtype).view(list(shape))
+        return best.view(dtype).view(list(shape))
+
+
+_SCOPES = threading.local()
+
+
+def _host_key(t):
+    return (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version)
+
+
+class stage_scope:
+    """Context manager for chains of calls on CPU tensors (`with interpol_b200.stage_scope(): ...`).
+
+    Inside the scope every distinct CPU tensor is uploaded ONCE (keyed on storage address, view
+    geometry and torch's version counter, so an in-place torch update re-uploads), and a CPU result
+    keeps its device twin: feeding it to the next call costs no transfer.  A registration step
+    (pull, then push back through the same grid) therefore moves volume + grid up and the two
+    results down, instead of uploading the grid twice and the pulled image once more.  The scope
+    keeps the host tensors it has seen alive until it exits; writes through aliases torch does not
+    track (numpy views) are not seen -- leave the scope, or call `.clear()`, after such writes.
+    """
+
+    def __init__(self):
+        self.twins = {}
+
+    def clear(self):
+        self.twins.clear()
+
+    def __enter__(self):
+        stack = getattr(_SCOPES, 'stack', None)
+        if stack is None:
+            stack = _SCOPES.stack = []
+        stack.append(self)
+        return self
+
+    def __exit__(self, *exc):
+        _SCOPES.stack.pop()
+        self.clear()
+        return False
+
+    def lookup(self, host, dev):
+        hit = self.twins.get(_host_key(host))
+        if hit is not None and hit[1].device == dev:
+            return hit[1]
+        return None
+
+    def remember(self, host, device_tensor):
+        self.twins[_host_key(host)] = (host, device_tensor)
+
+
+def _scope():
+    stack = getattr(_SCOPES, 'stack', None)
+    return stack[-1] if stack else None
 
 
 def _stage(*tensors):
@@ -70,8 +150,20 @@ def _stage(*tensors):
             dev = t.device
     if dev is None:
         dev = torch.device('cuda', torch.cuda.current_device())
-    staged = tuple(None if t is None else (t if t.is_cuda else t.to(dev, non_blocking=True))
-                   for t in tensors)
+    scope = _scope()
+
+    def up(t):
+        if t is None or t.is_cuda:
+            return t
+        if scope is not None and not t.requires_grad:
+            twin = scope.lookup(t, dev)
+            if twin is None:
+                twin = t.to(dev, non_blocking=True)
+                scope.remember(t, twin)
+            return twin
+        return t.to(dev, non_blocking=True)
+
+    staged = tuple(up(t) for t in tensors)
 
     def back(out):
         if out.requires_grad or out.numel() == 0:
@@ -81,6 +173,8 @@ def _stage(*tensors):
         host = _pinned_empty(out.shape, out.dtype)
         host.copy_(out, non_blocking=True)
         torch.cuda.current_stream(out.device).synchronize()
+        if scope is not None:
+            scope.remember(host, out)
         return host
 
     return staged, back

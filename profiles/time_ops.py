@@ -38,6 +38,7 @@ def main():
     ap.add_argument('--dtype', default='f32')
     ap.add_argument('--ops', default='pull,pull_generic,push,push_generic,count,grad,coeff')
     ap.add_argument('--incoherent', action='store_true')
+    ap.add_argument('--flags', type=int, default=0, help='IB200_FLAG_* bits for the non-generic ops (4: no pipe / box kernels)')
     ap.add_argument('--force-pipe', action='store_true', help='take the persistent kernels wherever they apply (IB200_FLAG_FORCE_PIPE)')
     a = ap.parse_args()
     peak, _ = measured_peak()
@@ -53,7 +54,7 @@ def main():
     b, o = [a.bound], [a.order]
     res = {}
     for op in a.ops.split(','):
-        pp.flags = 1 if op.endswith('_generic') else (8 if a.force_pipe else 0)
+        pp.flags = 1 if op.endswith('_generic') else (8 if a.force_pipe else a.flags)
         base = op.replace('_generic', '')
         if base == 'pull':
             fn = lambda: pp.grid_pull(vol, grid, b, o, 1); by = N * (3 * s + 2 * C * s)

@@ -31,7 +31,7 @@ def _case(order, seed, dtype=torch.float32, B=2, C=2, amp=3.0):
 
 
 def _tiled(name, op):
-    return name.startswith(op + '_tile3d') or name.startswith(op + '_pipe3d') or name.startswith(op + '_tap')
+    return any(name.startswith(op + sfx) for sfx in ('_tile3d', '_pipe3d', '_box3d'))
 
 
 @pytest.mark.parametrize('extrapolate', [1, 0, 2])

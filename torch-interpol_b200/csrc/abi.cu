@@ -175,6 +175,8 @@ static int run_scatter(int op, const ib200_problem *p, const void *img, const vo
         IB200_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(float), s));
         st = try_push_pipe(op, kp, p->dtype, img, grid, acc, s);
         if (st < 0) return st;
+        if (st == 0) st = try_push_box(op, kp, p->dtype, img, grid, acc, s);
+        if (st < 0) return st;
         if (st == 0) st = try_push_tiled(op, kp, p->dtype, img, grid, acc, s);
         if (st < 0) return st;
         if (st > 0) return half ? convert_from_f32(p->dtype, acc, out, n, s) : IB200_OK;

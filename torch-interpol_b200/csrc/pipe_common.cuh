@@ -396,9 +396,9 @@ static inline EncodeTiledFn tensor_map_encoder() {
     }
     return fn;
 }
-// float32 tensor of `rank` dims (innermost first), element strides `stride[1..rank-1]`
-static inline bool make_tensor_map(CUtensorMap *tm, const void *base, int rank, const long long *dim,
-                                   const long long *stride, const int *box) {
+// tensor of `rank` dims (innermost first) of `esize`-byte elements, element strides `stride[1..rank-1]`
+static inline bool make_tensor_map_t(CUtensorMap *tm, const void *base, int rank, const long long *dim,
+                                     const long long *stride, const int *box, CUtensorMapDataType dt, int esize) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return false;
     cuuint64_t gdim[5], gstr[4];
@@ -407,13 +407,17 @@ static inline bool make_tensor_map(CUtensorMap *tm, const void *base, int rank, 
         if (dim[i] < 1 || dim[i] > 0xffffffffLL) return false;
         gdim[i] = (cuuint64_t)dim[i]; bdim[i] = (cuuint32_t)box[i]; estr[i] = 1;
         if (i > 0) {
-            if (stride[i] <= 0 || (stride[i] * 4) % 16 != 0 || stride[i] * 4 >= (1LL << 40)) return false;
-            gstr[i - 1] = (cuuint64_t)stride[i] * 4;
+            if (stride[i] <= 0 || (stride[i] * esize) % 16 != 0 || stride[i] * esize >= (1LL << 40)) return false;
+            gstr[i - 1] = (cuuint64_t)stride[i] * esize;
         }
     }
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
+    return enc(tm, dt, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static inline bool make_tensor_map(CUtensorMap *tm, const void *base, int rank, const long long *dim,
+                                   const long long *stride, const int *box) {
+    return make_tensor_map_t(tm, base, rank, dim, stride, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
 }  // namespace ib200

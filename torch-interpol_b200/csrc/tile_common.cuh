@@ -83,7 +83,8 @@ struct TileGeom {
 
 // exact q / d for q * d < 2^32 with inv = floor(2^32 / d) + 1
 __device__ __forceinline__ int fast_div(int q, unsigned inv) { return inv ? (int)__umulhi((unsigned)q, inv) : q; }
-__host__ __device__ __forceinline__ unsigned make_inv(int d) { return d <= 1 ? 0u : (unsigned)(0x100000000ULL / (unsigned)d) + 1u; }
+// (32-bit form: 0xffffffff / d + 1 == floor(2^32 / d) + 1 unless d is a power of two, where it is 2^32 / d: exact too)
+__host__ __device__ __forceinline__ unsigned make_inv(int d) { return d <= 1 ? 0u : 0xffffffffu / (unsigned)d + 1u; }
 
 constexpr int kMaxExt = 160;      // longest tile edge the boundary tables hold
 constexpr int kIntMax = 0x7fffffff;
@@ -96,7 +97,8 @@ struct PlaneBox { int mn[3], mx[3]; };   // support starts of one x-plane of the
 // sit on different (x, y) rows never collide; the z origin is aligned to 4 words
 // so rows can be staged / flushed 16 bytes at a time.
 template <int ORDER>
-__device__ __forceinline__ TileGeom make_geom(const KParams &kp, const PlaneBox *pb, int p0, int p1, int cap) {
+__device__ __forceinline__ TileGeom make_geom(const KParams &kp, const PlaneBox *pb, int p0, int p1, int cap, int zround = 32,
+                                                int maxext = kMaxExt) {
     TileGeom g;
     bool any = true;
 #pragma unroll
@@ -109,10 +111,12 @@ __device__ __forceinline__ TileGeom make_geom(const KParams &kp, const PlaneBox 
         const long long e = (long long)b - a + 1 + ORDER;
         g.ext[d] = (int)(e > 0x3fffffff ? 0x3fffffff : e);
     }
-    g.sz = (int)(((long long)g.ext[2] + 31) & ~31LL);
+    g.sz = (int)(((long long)g.ext[2] + zround - 1) / zround * zround);
+    // zround == 16: lanes are tiled 2 rows x 16 z; an ODD multiple of 16 puts neighbouring rows 16 banks apart
+    if (zround == 16 && (g.sz & 16) == 0) g.sz += 16;
     g.sxy = g.sz * (g.ext[1] < 4096 ? g.ext[1] : 4096);
     const long long vol = (long long)g.sz * g.ext[1] * g.ext[0];
-    g.fits = any && g.ext[0] <= kMaxExt && g.ext[1] <= kMaxExt && g.ext[2] <= kMaxExt && vol <= cap;
+    g.fits = any && g.ext[0] <= maxext && g.ext[1] <= maxext && g.ext[2] <= maxext && vol <= cap;
     if (!any) { g.fits = 1; g.ext[0] = g.ext[1] = g.ext[2] = 0; g.sz = 32; g.sxy = 0; }
     bool plain = g.fits && any;
 #pragma unroll
@@ -125,7 +129,7 @@ __device__ __forceinline__ TileGeom make_geom(const KParams &kp, const PlaneBox 
     g.vpr = (g.ext[2] + 3) >> 2;
     g.inv_vpr = make_inv(g.vpr);
     g.inv_e1 = make_inv(g.ext[1]);
-    g.inv_cpr = make_inv(g.sz >> 5);
+    g.inv_cpr = make_inv(g.sz >> 5 > 0 ? g.sz >> 5 : 1);
     return g;
 }
 
@@ -217,7 +221,8 @@ __device__ __forceinline__ int start_of(float c) {
 constexpr int kExtraSlot = 6;
 template <typename T, int ORDER, int TX, int NT>
 __device__ __forceinline__ void plan_from_coords(const KParams &kp, const T *gtile, bool col_ok, int x0, int *red,
-                                                 PlaneBox *pb, TileGeom *geoms, int *nsub, int cap, float extra = 0.f) {
+                                                 PlaneBox *pb, TileGeom *geoms, int *nsub, int cap, float extra = 0.f,
+                                                 int zround = 32, int maxext = kMaxExt) {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool masked = kp.extrapolate != 1;
@@ -279,7 +284,7 @@ __device__ __forceinline__ void plan_from_coords(const KParams &kp, const T *gti
     __syncthreads();
     if (threadIdx.x == 0) {
         pb[0] = combine(0);
-        geoms[0] = make_geom<ORDER>(kp, pb, 0, 1, cap);
+        geoms[0] = make_geom<ORDER>(kp, pb, 0, 1, cap, zround, maxext);
         *nsub = geoms[0].fits ? 1 : 0;
         unsigned e = 0;
         for (int w = 0; w < NW; ++w) e = max(e, (unsigned)red[w * 8 + kExtraSlot]);
@@ -300,7 +305,7 @@ __device__ __forceinline__ void plan_from_coords(const KParams &kp, const T *gti
             bool ok = true;
             const int per = TX / ns;
             for (int s = 0; s < ns; ++s) {
-                geoms[s] = make_geom<ORDER>(kp, pb, s * per, (s + 1) * per, cap);
+                geoms[s] = make_geom<ORDER>(kp, pb, s * per, (s + 1) * per, cap, zround, maxext);
                 ok = ok && geoms[s].fits;
             }
             if (ok || ns == TX) break;

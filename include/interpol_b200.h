@@ -152,6 +152,13 @@ IB200_API int ib200_pushgrad(const ib200_problem *p, const void *img, const void
 IB200_API int ib200_pull_backward_grid(const ib200_problem *p, const void *vol, const void *grid,
                              const void *gout, void *out, void *stream);
 
+/* Fused backward of grad w.r.t. the grid: out (B, *pts_shape, D)[d] =
+ * sum_c sum_e hess(vol, grid)[b,c,...,d,e] * gout[b,c,...,e] without materialising the
+ * (B, C, *pts, D, D) Hessian of pushpull.grid_grad_backward
+ * (interpol/pushpull.py:318-324).  `gout` uses img_stride (B, C, X, Y, Z, D). */
+IB200_API int ib200_grad_backward_grid(const ib200_problem *p, const void *vol, const void *grid,
+                             const void *gout, void *out, void *stream);
+
 /* Number of bytes of scratch the scatter entry points need for this problem
  * (0 for F32/F64). */
 IB200_API size_t ib200_scratch_bytes(const ib200_problem *p);

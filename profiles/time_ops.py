@@ -64,6 +64,13 @@ def main():
             fn = lambda: pp.grid_count(grid, [n] * 3, b, o, 1); by = N * (3 * s + s)
         elif base == 'grad':
             fn = lambda: pp.grid_grad(vol, grid, b, o, 1); by = N * (3 * s + C * s + 3 * C * s)
+        elif base == 'bwd':          # GridPull.backward: push(grad) + fused sum_c grad(vol) * grad
+            vr, gr = vol.clone().requires_grad_(), grid.clone().requires_grad_()
+            gout = torch.randn_like(vol)
+            fn = lambda: pp.grid_pull_backward(gout, vr, gr, b, o, 1); by = N * (3 * s + 2 * C * s) + N * (3 * s + 2 * C * s + 3 * s)
+        elif base == 'bwd_grid':     # grid branch alone
+            gout = torch.randn_like(vol)
+            fn = lambda: pp.grid_pull_grad_grid(gout, vol, grid, b, o, 1); by = N * (3 * s + 2 * C * s + 3 * s)
         elif base == 'coeff':
             fn = lambda: ib.spline_coeff_nd(vol, interpolation=a.order, bound=a.bound, dim=3); by = 2 * C * N * s
         else:

@@ -257,3 +257,79 @@ def test_headline_256_vs_oracle():
     v64, g64 = to_np(vol), to_np(grid)
     assert rel_err(to_np(pull), oracle.grid_pull(v64, g64, [3], [3], 1)) <= 1e-5, k
     assert rel_err(to_np(push), oracle.grid_push(to_np(pull), g64, [256] * 3, [3], [3], 1, nthreads=8)) <= 1e-5
+
+
+# ------------------------------------------------------------ fused backward --
+
+@pytest.mark.parametrize('channels', [1, 3])
+@pytest.mark.parametrize('order', [1, 3, 5])
+def test_fused_backward_vs_oracle_composition(order, channels):
+    """GridPull / GridPush / GridCount / GridGrad backward at tiled sizes against the reference's algebra
+    (pushpull.py:237-325) evaluated with the float64 oracle: push(grad) + sum_c grad(vol) * grad_out, etc.
+    The grid branch runs the fused kernels (pullbwd_pipe3d / pullbwd_tile3d; no (B,C,N,D) temporary)."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    gen = torch.Generator().manual_seed(1300 + 10 * order + channels)
+    B = 2
+    vol = torch.randn([B, channels, *VSHAPE], generator=gen)
+    grid = smooth_grid(SHAPE, gen, amp=3.0, batch=B)
+    grid = (grid * torch.tensor([VSHAPE[d] / SHAPE[d] for d in range(3)]) - 1.25).contiguous()
+    gout = torch.randn([B, channels, *SHAPE], generator=gen)
+    bound, o, ex = [3, 6, 1], [order], 1
+    v64, g64, o64 = vol.double().numpy(), grid.double().numpy(), gout.double().numpy()
+    # ---- pull
+    v = vol.cuda().requires_grad_(); g = grid.cuda().requires_grad_()
+    gi, gg = pp.grid_pull_backward(gout.cuda(), v, g, bound, o, ex)
+    assert ib.last_kernel().startswith(('pullbwd_tile3d', 'pullbwd_pipe3d')), ib.last_kernel()
+    want_gi = oracle.grid_push(o64, g64, VSHAPE, bound, o, ex)
+    want_gg = (oracle.grid_grad(v64, g64, bound, o, ex) * o64[..., None]).sum(1)
+    assert rel_err(to_np(gi), want_gi) <= 1e-5
+    assert rel_err(to_np(gg), want_gg) <= 1e-5
+    # ---- push (roles swapped: inp lives on the lattice, grad on the volume)
+    img = gout.cuda().requires_grad_()
+    gvol = vol.cuda()
+    gi, gg = pp.grid_push_backward(gvol, img, g, bound, o, ex)
+    assert ib.last_kernel().startswith(('pullbwd_tile3d', 'pullbwd_pipe3d')), ib.last_kernel()
+    assert rel_err(to_np(gi), oracle.grid_pull(v64, g64, bound, o, ex)) <= 1e-5
+    assert rel_err(to_np(gg), want_gg) <= 1e-5
+    # ---- count: grad (B, 1, *vshape)
+    gcnt = vol[:, :1].cuda()
+    gg = pp.grid_count_backward(gcnt, g, bound, o, ex)
+    want = oracle.grid_grad(v64[:, :1], g64, bound, o, ex)[:, 0]
+    assert rel_err(to_np(gg), want) <= 1e-5
+    # ---- grad: gout (B, C, *shape, 3); fused Hessian contraction (generic kernel, no (B,C,N,3,3) temporary)
+    gout3 = torch.randn([B, channels, *SHAPE, 3], generator=gen)
+    gi, gg = pp.grid_grad_backward(gout3.cuda(), v, g, bound, o, ex)
+    assert ib.last_kernel().startswith('gather_grad_bwd_grid'), ib.last_kernel()
+    o3 = gout3.double().numpy()
+    assert rel_err(to_np(gi), oracle.grid_pushgrad(o3, g64, VSHAPE, bound, o, ex)) <= 1e-5
+    hess = oracle.grid_hess(v64, g64, bound, o, ex)
+    want = (hess * o3[..., None]).sum(axis=(1, -2))
+    if np.abs(want).max() > 0:
+        assert rel_err(to_np(gg), want) <= 1e-5
+    else:
+        assert np.abs(to_np(gg)).max() == 0
+
+
+def test_fused_backward_full_size():
+    """256^3 cubic, C = 1 (the headline shape): autograd through grid_pull, grid branch on the persistent
+    fused kernel, checked against the unfused composition on the GPU and (grid branch) the oracle."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    bench = _bench()
+    vol, grid = bench.make_workload(256, 'cuda')
+    gout = torch.randn(vol.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    v = vol.clone().requires_grad_(); g = grid.clone().requires_grad_()
+    out = ib.grid_pull(v, g, interpolation=3, bound='dct2', extrapolate=True)
+    out.backward(gout)            # (runs on the autograd thread: the per-thread launch log is checked below)
+    _, gg2 = pp.grid_pull_backward(gout, v.detach().requires_grad_(), g.detach().requires_grad_(), [3], [3], 1)
+    assert ib.last_kernel().startswith('pullbwd_pipe3d'), ib.last_kernel()
+    assert torch.equal(gg2, g.grad)
+    ref_gg = pp.grid_grad(vol, grid, [3], [3], 1)[:, 0] * gout[0, 0, ..., None]
+    assert rel_err(to_np(g.grad), to_np(ref_gg)) <= 1e-6
+    ref_gi = pp.grid_push(gout, grid, [256] * 3, [3], [3], 1)
+    assert rel_err(to_np(v.grad), to_np(ref_gi)) <= 1e-6
+    want = oracle.grid_grad(to_np(vol), to_np(grid), [3], [3], 1)[:, 0] * to_np(gout)[0, 0, ..., None]
+    assert rel_err(to_np(g.grad), want) <= 1e-5

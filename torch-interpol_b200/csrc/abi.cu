@@ -127,18 +127,19 @@ static int build_params(const ib200_problem *p, int need, KParams &kp) {
 static int run_gather(int op, const ib200_problem *p, const void *vol, const void *grid,
                       const void *gout, void *out, void *stream) {
     KParams kp;
-    int need = NEED_VOL_IN | (op == OP_PULL_BWD_GRID ? NEED_IMG_IN : 0);
+    const bool fused_bwd = op == OP_PULL_BWD_GRID || op == OP_GRAD_BWD_GRID;
+    int need = NEED_VOL_IN | (fused_bwd ? NEED_IMG_IN : 0) | (op == OP_GRAD_BWD_GRID ? IMG_HAS_COMP : 0);
     int st = build_params(p, need, kp);
     if (st != IB200_OK) return st;
-    if (kp.batch * kp.pts_total == 0 || (kp.channels == 0 && op != OP_PULL_BWD_GRID)) return IB200_OK;
-    if (!vol || !grid || !out || (op == OP_PULL_BWD_GRID && !gout)) return IB200_ERR_NULL;
+    if (kp.batch * kp.pts_total == 0 || (kp.channels == 0 && !fused_bwd)) return IB200_OK;
+    if (!vol || !grid || !out || (fused_bwd && !gout)) return IB200_ERR_NULL;
     DeviceGuard guard(p->device);
     if (!guard.ok) return IB200_ERR_CUDA - (int)cudaErrorInvalidDevice;
     cudaStream_t s = (cudaStream_t)stream;
-    if ((op == OP_PULL || op == OP_GRAD) && !(p->flags & IB200_FLAG_NO_TILES)) {
-        st = try_pull_pipe(op, kp, p->dtype, vol, grid, out, s);
+    if ((op == OP_PULL || op == OP_GRAD || op == OP_PULL_BWD_GRID) && !(p->flags & IB200_FLAG_NO_TILES)) {
+        st = try_pull_pipe(op, kp, p->dtype, vol, grid, gout, out, s);
         if (st != 0) return st < 0 ? st : IB200_OK;
-        st = try_pull_tiled(op, kp, p->dtype, vol, grid, out, s);
+        st = try_pull_tiled(op, kp, p->dtype, vol, grid, gout, out, s);
         if (st != 0) return st < 0 ? st : IB200_OK;
     }
     switch (p->dtype) {
@@ -211,6 +212,11 @@ int ib200_hess(const ib200_problem *p, const void *vol, const void *grid, void *
 int ib200_pull_backward_grid(const ib200_problem *p, const void *vol, const void *grid,
                              const void *gout, void *out, void *stream) {
     return run_gather(OP_PULL_BWD_GRID, p, vol, grid, gout, out, stream);
+}
+
+int ib200_grad_backward_grid(const ib200_problem *p, const void *vol, const void *grid,
+                             const void *gout, void *out, void *stream) {
+    return run_gather(OP_GRAD_BWD_GRID, p, vol, grid, gout, out, stream);
 }
 
 int ib200_push(const ib200_problem *p, const void *img, const void *grid, void *vol_out,

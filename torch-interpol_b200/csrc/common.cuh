@@ -105,9 +105,10 @@ IB200_DECL_LAUNCHERS(bf16)
 int launch_coeff(void *data, int dtype, i64 outer, i64 n, i64 inner, int bound, int order,
                  cudaStream_t stream);
 // tiled fast paths: return 1 when they handled the call, 0 when not applicable, <0 on error
-int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out,
+// (`gout`: lattice image the fused backward OP_PULL_BWD_GRID multiplies the gradient with, NULL otherwise)
+int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const void *grid, const void *gout, void *out,
                    cudaStream_t stream);
-int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out,
+int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const void *grid, const void *gout, void *out,
                   cudaStream_t stream);
 bool push_tiled_applicable(int op, const KParams &kp, int dtype);
 int try_push_tiled(int op, const KParams &kp, int dtype, const void *img, const void *grid,
@@ -124,7 +125,7 @@ int launch_resample_adjoint(const KParams &kp, int dtype, const void *in, void *
                             i64 n_out, i64 inner, int order, int bound, int extrapolate, cudaStream_t stream);
 int launch_pull_labels(const KParams &kp, int grid_dtype, const void *vol, const void *grid, void *out, cudaStream_t stream);
 
-enum { OP_PULL = 0, OP_GRAD = 1, OP_HESS = 2, OP_PULL_BWD_GRID = 3 };
+enum { OP_PULL = 0, OP_GRAD = 1, OP_HESS = 2, OP_PULL_BWD_GRID = 3, OP_GRAD_BWD_GRID = 4 };
 enum { OP_PUSH = 0, OP_COUNT = 1, OP_PUSHGRAD = 2 };
 
 }  // namespace ib200

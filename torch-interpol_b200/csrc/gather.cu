@@ -33,14 +33,15 @@ __device__ __forceinline__ void decompose(const KParams &kp, i64 p, i64 &b, int 
     }
 }
 
-// OP: OP_PULL / OP_GRAD / OP_HESS / OP_PULL_BWD_GRID
+// OP: OP_PULL / OP_GRAD / OP_HESS / OP_PULL_BWD_GRID / OP_GRAD_BWD_GRID
 template <typename T, int DIM, int ORDER, int OP>
 __global__ void __launch_bounds__(256)
 gather_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
               const T *__restrict__ grid, const T *__restrict__ gout, T *__restrict__ out) {
     typedef typename Traits<T>::Real R;
     constexpr int NODES = ORDER >= 0 ? ORDER + 1 : 8;
-    constexpr int NEED = (OP == OP_PULL) ? 0 : (OP == OP_HESS ? 2 : 1);
+    constexpr bool HESS = (OP == OP_HESS || OP == OP_GRAD_BWD_GRID);   // second derivatives needed
+    constexpr int NEED = (OP == OP_PULL) ? 0 : (HESS ? 2 : 1);
     constexpr int NH = DIM * (DIM + 1) / 2;
     constexpr int UNR = ORDER >= 0 ? NODES : 1;   // never unroll the runtime-order loops
 
@@ -74,7 +75,7 @@ gather_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
             else unit_axis(ax[d]);
         }
 
-        R bwd[DIM];   // OP_PULL_BWD_GRID accumulates over channels
+        R bwd[DIM];   // OP_PULL_BWD_GRID / OP_GRAD_BWD_GRID accumulate over channels
 #pragma unroll
         for (int d = 0; d < DIM; ++d) bwd[d] = R(0);
 
@@ -117,7 +118,7 @@ gather_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
                     if (OP == OP_PULL) acc0 = fma(wx, s00, acc0);
                     if (NEED >= 1) {
                         const R gx = ax[0].g[i];
-                        if (OP != OP_HESS) {
+                        if (!HESS) {
                             accg[0] = fma(gx, s00, accg[0]);
                             if (DIM >= 2) accg[1 % DIM] = fma(wx, s10, accg[1 % DIM]);
                             if (DIM >= 3) accg[2 % DIM] = fma(wx, s01, accg[2 % DIM]);
@@ -159,13 +160,28 @@ gather_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
                     Traits<T>::store(o + 3, acch[1 % NH]); Traits<T>::store(o + 4, acch[3 % NH]); Traits<T>::store(o + 5, acch[4 % NH]);
                     Traits<T>::store(o + 6, acch[2 % NH]); Traits<T>::store(o + 7, acch[4 % NH]); Traits<T>::store(o + 8, acch[5 % NH]);
                 }
-            } else {   // OP_PULL_BWD_GRID: sum_c grad * gout   (pushpull.py:257)
+            } else if (OP == OP_PULL_BWD_GRID) {   // sum_c grad * gout   (pushpull.py:257)
                 const R go = Traits<T>::load(gout + b * kp.img_sb + c * kp.img_sc + ioff);
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) bwd[d] = fma(accg[d], go, bwd[d]);
+            } else {   // OP_GRAD_BWD_GRID: sum_c hess . gout  (pushpull.py:321-324), gout (B, C, *pts, D)
+                const T *gp = gout + b * kp.img_sb + c * kp.img_sc + (kp.pts_dense ? ioff * DIM : ioff);
+                R go[DIM];
+#pragma unroll
+                for (int e = 0; e < DIM; ++e) go[e] = Traits<T>::load(gp + e * kp.img_sd);
+                if (DIM == 1) {
+                    bwd[0] = fma(acch[0], go[0], bwd[0]);
+                } else if (DIM == 2) {
+                    bwd[0] = fma(acch[0], go[0], fma(acch[1 % NH], go[1 % DIM], bwd[0]));
+                    bwd[1 % DIM] = fma(acch[1 % NH], go[0], fma(acch[2 % NH], go[1 % DIM], bwd[1 % DIM]));
+                } else {
+                    bwd[0] = fma(acch[0], go[0], fma(acch[1 % NH], go[1 % DIM], fma(acch[2 % NH], go[2 % DIM], bwd[0])));
+                    bwd[1 % DIM] = fma(acch[1 % NH], go[0], fma(acch[3 % NH], go[1 % DIM], fma(acch[4 % NH], go[2 % DIM], bwd[1 % DIM])));
+                    bwd[2 % DIM] = fma(acch[2 % NH], go[0], fma(acch[4 % NH], go[1 % DIM], fma(acch[5 % NH], go[2 % DIM], bwd[2 % DIM])));
+                }
             }
         }
-        if (OP == OP_PULL_BWD_GRID) {
+        if (OP == OP_PULL_BWD_GRID || OP == OP_GRAD_BWD_GRID) {
             T *o = out + (b * kp.pts_total + r_dense) * DIM;
 #pragma unroll
             for (int d = 0; d < DIM; ++d) Traits<T>::store(o + d, bwd[d]);
@@ -175,7 +191,7 @@ gather_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
 
 // ---------------------------------------------------------------- launch --
 
-static const char *kOpName[4] = {"pull", "grad", "hess", "pull_bwd_grid"};
+static const char *kOpName[5] = {"pull", "grad", "hess", "pull_bwd_grid", "grad_bwd_grid"};
 
 template <typename T, int DIM, int ORDER, int OP>
 static int launch_one(const KParams &kp, const void *vol, const void *grid, const void *gout,
@@ -201,7 +217,7 @@ static int dispatch_order(const KParams &kp, const void *vol, const void *grid, 
     bool iso = true;
     for (int d = 1; d < DIM; ++d) iso = iso && kp.order[d] == kp.order[0];
     // the order-1 closed forms depend on kp flags only; compile-time orders are safe
-    if (iso && OP != OP_HESS) {
+    if (iso && OP != OP_HESS && OP != OP_GRAD_BWD_GRID) {
         switch (kp.order[0]) {
 #define IB200_CASE(O) case O: return launch_one<T, DIM, O, OP>(kp, vol, grid, gout, out, stream);
         IB200_STATIC_ORDERS(IB200_CASE)
@@ -231,6 +247,7 @@ static int dispatch_op(int op, const KParams &kp, const void *vol, const void *g
     case OP_GRAD: return dispatch_dim<T, OP_GRAD>(kp, vol, grid, gout, out, stream);
     case OP_HESS: return dispatch_dim<T, OP_HESS>(kp, vol, grid, gout, out, stream);
     case OP_PULL_BWD_GRID: return dispatch_dim<T, OP_PULL_BWD_GRID>(kp, vol, grid, gout, out, stream);
+    case OP_GRAD_BWD_GRID: return dispatch_dim<T, OP_GRAD_BWD_GRID>(kp, vol, grid, gout, out, stream);
     }
     return IB200_ERR_NULL;
 }

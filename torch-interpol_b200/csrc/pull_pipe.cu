@@ -22,6 +22,7 @@
 // matter for throughput; pull_tile.cu / gather.cu cover the rest.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include "pipe_common.cuh"
 
 namespace ib200 {
@@ -37,7 +38,7 @@ constexpr int kNB = 2;     // ring of boxes
 
 template <int ORDER, int OP, int W>
 __device__ __noinline__ float3 pull_point_global(const KParams &kp, const float *src, float c0, float c1, float c2) {
-    constexpr bool GRAD = (OP == OP_GRAD);
+    constexpr bool GRAD = (OP == OP_GRAD || OP == OP_PULL_BWD_GRID);
     const float cc[3] = {c0, c1, c2};
     float acc = 0.f, ag[3] = {0.f, 0.f, 0.f};
     if (inbounds<float, 3>(kp, cc)) {
@@ -73,13 +74,14 @@ template <int ORDER, int OP, int NCW>
 __global__ void __launch_bounds__(32 * (NCW + 1), 1)
 pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_grid, const float *__restrict__ vol,
-                   float *__restrict__ out, const int ntiles, const int cmul, const int bmul, const int gbmul,
+                   const float *__restrict__ gout, float *__restrict__ out, const int ntiles, const int cmul, const int bmul, const int gbmul,
                    const unsigned inv_ntz, const unsigned inv_nty, const unsigned inv_ntx, long long *dbg) {
     constexpr int TX = 8, TY = 8, TZ = 32;
     constexpr int NPT = TX * TY * TZ;
     constexpr int NROWS = TX * TY;
     constexpr int W = ORDER + 1;
-    constexpr bool GRAD = (OP == OP_GRAD);
+    constexpr bool GRAD = (OP == OP_GRAD || OP == OP_PULL_BWD_GRID);
+    constexpr bool BWD = (OP == OP_PULL_BWD_GRID);     // fused backward w.r.t. the grid: grad * gout (one channel)
     constexpr int NCT = NCW * 32;                  // consumer threads
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *box = reinterpret_cast<float *>(smem_raw);                                   // [kNB][kBoxWords]
@@ -252,6 +254,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
             for (int c = 0; c < C; ++c) {
                 const float *src = vol + (i64)b * kp.vol_sb + (i64)c * kp.vol_sc;
                 float *dst = out + ((i64)b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1);
+                const float *gm = BWD ? gout + (i64)b * kp.img_sb + (i64)c * kp.img_sc : nullptr;
                 bool last;
                 do {
                     const int s = n % kNB;
@@ -401,6 +404,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                                 }
                             }
                             const int o = ((x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lane);
+                            if (BWD) { const float m = gm[o]; res[0] *= m; res[1] *= m; res[2] *= m; }
                             if (!GRAD) dst[o] = res[0];
                             else { dst[o * 3] = res[0]; dst[o * 3 + 1] = res[1]; dst[o * 3 + 2] = res[2]; }
                         }
@@ -438,13 +442,18 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
 // ---------------------------------------------------------------- launch --
 
 template <int ORDER, int OP, int NCW>
-static int launch_pull_pipe(const KParams &kp, const float *vol, const float *grid, float *out, cudaStream_t stream) {
+static int launch_pull_pipe(const KParams &kp, const float *vol, const float *grid, const float *gout, float *out, cudaStream_t stream) {
     constexpr int NPT = 8 * 8 * 32;
     const size_t smem_total = (size_t)kNB * kBoxWords * 4 + (size_t)kNG * NPT * 3 * 4 + kNB * sizeof(PipeGeom) +
                               (2 * kNG + 2 * kNB + 2) * sizeof(unsigned long long) + (3 * kNB + 40) * sizeof(int) + 4 * sizeof(PipeGeom) + (size_t)kNB * kZLut * 8 + 64;
     const i64 ntiles = kp.batch * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
     if (ntiles == 0) return 1;
     if (ntiles * kp.channels > 0x3fffffffLL) return 0;
+    // the tile decode divides by multiply-high: exact only while tile * divisor < 2^32
+    {
+        const i64 dmax = std::max<i64>((kp.pts_n[2] + 31) / 32, std::max<i64>((kp.pts_n[1] + 7) / 8, (kp.pts_n[0] + 7) / 8));
+        if (ntiles * dmax >= (1LL << 32)) return 0;
+    }
     // tensor maps: volume (z, y, x, c, b), box {64, 16, 1, 1, 1}; grid (z*3, y, x, b), box {96, 8, 8, 1}
     CUtensorMap tm_vol, tm_grid;
     const long long vbytes = (((long long)kp.vol_n[0] * kp.vol_s[0]) + 3) & ~3LL;
@@ -469,17 +478,18 @@ static int launch_pull_pipe(const KParams &kp, const float *vol, const float *gr
     const int nblocks = (int)(ntiles < pipe_sm_count() ? ntiles : pipe_sm_count());
     long long *dbg = nullptr;
     if (getenv("IB200_PIPE_DEBUG")) IB200_CUDA_CHECK(cudaGetSymbolAddress((void **)&dbg, g_pipe_dbg));
-    kern<<<nblocks, 32 * (NCW + 1), smem_total, stream>>>(kp, tm_vol, tm_grid, vol, out, (int)ntiles, cmul, bmul, gbmul,
+    kern<<<nblocks, 32 * (NCW + 1), smem_total, stream>>>(kp, tm_vol, tm_grid, vol, gout, out, (int)ntiles, cmul, bmul, gbmul,
         make_inv((kp.pts_n[2] + 31) / 32), make_inv((kp.pts_n[1] + 7) / 8), make_inv((kp.pts_n[0] + 7) / 8), dbg);
     static thread_local char name[64];
-    snprintf(name, sizeof(name), "%s_pipe3d_o%d", OP == OP_GRAD ? "grad" : "pull", ORDER);
+    snprintf(name, sizeof(name), "%s_pipe3d_o%d", OP == OP_GRAD ? "grad" : OP == OP_PULL_BWD_GRID ? "pullbwd" : "pull", ORDER);
     note_launch(name);
     IB200_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
 
-int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out, cudaStream_t stream) {
-    if (op != OP_PULL && op != OP_GRAD) return 0;
+int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const void *grid, const void *gout_, void *out, cudaStream_t stream) {
+    if (op != OP_PULL && op != OP_GRAD && op != OP_PULL_BWD_GRID) return 0;
+    if (op == OP_PULL_BWD_GRID && (kp.channels != 1 || !gout_)) return 0;        // several channels: the tile kernel sums them
     if (dtype != IB200_F32) return 0;
     if (kp.dim != 3 || !kp.pts_dense) return 0;
     if (kp.order[0] != kp.order[1] || kp.order[0] != kp.order[2]) return 0;
@@ -500,20 +510,26 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
     if ((uintptr_t)vol % 16 || (uintptr_t)grid % 16) return 0;
     if (kp.vol_s[0] % 4 || kp.vol_s[1] % 4 || kp.vol_sb % 4 || kp.vol_sc % 4) return 0;
     if (kp.pts_n[2] % 4 || kp.grid_sb % 4) return 0;
-    const float *v = (const float *)vol, *g = (const float *)grid;
+    const float *v = (const float *)vol, *g = (const float *)grid, *go = (const float *)gout_;
     float *o = (float *)out;
     constexpr int NCW = 15;
     if (op == OP_PULL) {
         switch (kp.order[0]) {
-        case 1: return launch_pull_pipe<1, OP_PULL, NCW>(kp, v, g, o, stream);
-        case 2: return launch_pull_pipe<2, OP_PULL, NCW>(kp, v, g, o, stream);
-        case 3: return launch_pull_pipe<3, OP_PULL, NCW>(kp, v, g, o, stream);
+        case 1: return launch_pull_pipe<1, OP_PULL, NCW>(kp, v, g, nullptr, o, stream);
+        case 2: return launch_pull_pipe<2, OP_PULL, NCW>(kp, v, g, nullptr, o, stream);
+        case 3: return launch_pull_pipe<3, OP_PULL, NCW>(kp, v, g, nullptr, o, stream);
+        }
+    } else if (op == OP_PULL_BWD_GRID) {
+        switch (kp.order[0]) {
+        case 1: return launch_pull_pipe<1, OP_PULL_BWD_GRID, NCW>(kp, v, g, go, o, stream);
+        case 2: return launch_pull_pipe<2, OP_PULL_BWD_GRID, NCW>(kp, v, g, go, o, stream);
+        case 3: return launch_pull_pipe<3, OP_PULL_BWD_GRID, NCW>(kp, v, g, go, o, stream);
         }
     } else {
         switch (kp.order[0]) {
-        case 1: return launch_pull_pipe<1, OP_GRAD, NCW>(kp, v, g, o, stream);
-        case 2: return launch_pull_pipe<2, OP_GRAD, NCW>(kp, v, g, o, stream);
-        case 3: return launch_pull_pipe<3, OP_GRAD, NCW>(kp, v, g, o, stream);
+        case 1: return launch_pull_pipe<1, OP_GRAD, NCW>(kp, v, g, nullptr, o, stream);
+        case 2: return launch_pull_pipe<2, OP_GRAD, NCW>(kp, v, g, nullptr, o, stream);
+        case 3: return launch_pull_pipe<3, OP_GRAD, NCW>(kp, v, g, nullptr, o, stream);
         }
     }
     return 0;

@@ -30,12 +30,15 @@ namespace ib200 {
 template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
-                   const T *__restrict__ grid, T *__restrict__ out, const int cap, const int vec_ok) {
+                   const T *__restrict__ grid, const T *__restrict__ gout, T *__restrict__ out, const int cap, const int vec_ok) {
     constexpr int NPT = TX * TY * TZ;            // points per tile
     constexpr int W = ORDER + 1;
     constexpr int NW = NT / 32;
     constexpr bool F32 = sizeof(T) == 4;
-    constexpr bool GRAD = (OP == OP_GRAD);
+    constexpr bool GRAD = (OP == OP_GRAD || OP == OP_PULL_BWD_GRID);
+    // fused backward w.r.t. the grid (pushpull.py:254-257): out (B, N, 3) = sum_c grad_c * gout_c; a thread owns the
+    // same voxels for every channel, so the sum is a plain read-modify-write of its own output
+    constexpr bool BWD = (OP == OP_PULL_BWD_GRID);
     constexpr int UI = ORDER <= 3 ? W : 1, UJ = ORDER <= 5 ? W : 1;   // keep the code of high orders compact
     static_assert(NT == TY * TZ, "one thread per (y, z) column of the tile; x-planes are looped");
     static_assert(TZ % 4 == 0, "z rows are staged 16 bytes at a time");
@@ -64,7 +67,7 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
     stage_grid_tile<T, TX, TY, TZ, NT>(kp, grid + b * kp.grid_sb, gtile, x0, y0, z0, nzv, vec_ok);
     cp_async_wait_all();
     __syncthreads();
-    plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap);
+    plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap, 0.f, TZ == 16 ? 16 : 32);
     const int nsub = *nsub_p;
     const int per = TX / nsub;
 
@@ -72,11 +75,11 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
         const TileGeom g = geoms[s];
         if (g.ext[0] == 0 && g.fits) {
             // nothing in bounds in this group: zeros
-            for (i64 c = 0; c < kp.channels; ++c)
+            for (i64 c = 0; c < (BWD ? 1 : kp.channels); ++c)
                 for (int p = s * per; p < (s + 1) * per; ++p)
                     if (col_ok && x0 + p < kp.pts_n[0]) {
                         const i64 r = ((i64)(x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lz);
-                        T *dst = out + ((b * kp.channels + c) * kp.pts_total + r) * (GRAD ? 3 : 1);
+                        T *dst = out + ((b * (BWD ? 1 : kp.channels) + c) * kp.pts_total + r) * (GRAD ? 3 : 1);
                         Traits<T>::store(dst, 0.f);
                         if (GRAD) { Traits<T>::store(dst + 1, 0.f); Traits<T>::store(dst + 2, 0.f); }
                     }
@@ -85,7 +88,8 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
         if (g.fits) { __syncthreads(); build_tables<NT>(kp, g, idx_tab, sgn_tab); }
         for (i64 c = 0; c < kp.channels; ++c) {
             const T *src = vol + b * kp.vol_sb + c * kp.vol_sc;
-            T *dst = out + (b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1);
+            T *dst = out + (BWD ? b : b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1);
+            const T *gm = BWD ? gout + b * kp.img_sb + c * kp.img_sc : nullptr;
             if (g.fits) {
                 // ---- 3. stage the box, one 4-word vector per thread -------------------
                 // x / y folding comes from the per-axis tables (row base, row sign).  A
@@ -159,6 +163,11 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
                         }
                     }
                     const i64 r = ((i64)(x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lz);
+                    if (BWD) {
+                        const float m = Traits<T>::load(gm + r);
+                        ax_ *= m; ay_ *= m; az_ *= m;
+                        if (c > 0) { ax_ += Traits<T>::load_rw(dst + r * 3); ay_ += Traits<T>::load_rw(dst + r * 3 + 1); az_ += Traits<T>::load_rw(dst + r * 3 + 2); }
+                    }
                     if (!GRAD) Traits<T>::store(dst + r, acc);
                     else { Traits<T>::store(dst + r * 3, ax_); Traits<T>::store(dst + r * 3 + 1, ay_); Traits<T>::store(dst + r * 3 + 2, az_); }
                 }
@@ -197,6 +206,11 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
                         }
                     }
                     const i64 r = ((i64)(x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lz);
+                    if (BWD) {
+                        const float m = Traits<T>::load(gm + r);
+                        ag[0] *= m; ag[1] *= m; ag[2] *= m;
+                        if (c > 0) { ag[0] += Traits<T>::load_rw(dst + r * 3); ag[1] += Traits<T>::load_rw(dst + r * 3 + 1); ag[2] += Traits<T>::load_rw(dst + r * 3 + 2); }
+                    }
                     if (!GRAD) Traits<T>::store(dst + r, acc);
                     else { Traits<T>::store(dst + r * 3, ag[0]); Traits<T>::store(dst + r * 3 + 1, ag[1]); Traits<T>::store(dst + r * 3 + 2, ag[2]); }
                 }
@@ -208,7 +222,7 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
 // ---------------------------------------------------------------- launch --
 
 template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MINB>
-static int launch_pull_tile_cfg(const KParams &kp, const void *vol, const void *grid, void *out, cudaStream_t stream,
+static int launch_pull_tile_cfg(const KParams &kp, const void *vol, const void *grid, const void *gout, void *out, cudaStream_t stream,
                                 size_t smem_total) {
     const size_t fixed = (size_t)TX * TY * TZ * 3 * sizeof(T) + 3 * kMaxExt * (sizeof(int) + sizeof(float)) +
                          TX * (NT / 32) * 8 * sizeof(int) + TX * (sizeof(PlaneBox) + sizeof(TileGeom)) + 32;
@@ -223,48 +237,49 @@ static int launch_pull_tile_cfg(const KParams &kp, const void *vol, const void *
                         ((kp.pts_n[2] * 3) % ev == 0) && (kp.grid_sb % ev == 0);
     auto kern = pull_tile3d_kernel<T, ORDER, OP, TX, TY, TZ, NT, MINB>;
     IB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
-    kern<<<(unsigned)ntiles, NT, smem_total, stream>>>(kp, (const T *)vol, (const T *)grid, (T *)out, cap, vec_ok ? 1 : 0);
+    kern<<<(unsigned)ntiles, NT, smem_total, stream>>>(kp, (const T *)vol, (const T *)grid, (const T *)gout, (T *)out, cap, vec_ok ? 1 : 0);
     static thread_local char name[64];
-    snprintf(name, sizeof(name), "%s_tile3d_o%d_%dx%dx%d", OP == OP_GRAD ? "grad" : "pull", ORDER, TX, TY, TZ);
+    snprintf(name, sizeof(name), "%s_tile3d_o%d_%dx%dx%d", OP == OP_GRAD ? "grad" : OP == OP_PULL_BWD_GRID ? "pullbwd" : "pull", ORDER, TX, TY, TZ);
     note_launch(name);
     IB200_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
 
 template <typename T, int ORDER, int OP>
-static int launch_pull_tile(const KParams &kp, const void *vol, const void *grid, void *out, cudaStream_t stream) {
+static int launch_pull_tile(const KParams &kp, const void *vol, const void *grid, const void *gout, void *out, cudaStream_t stream) {
 #ifdef IB200_TUNE
     const char *e = getenv("IB200_VARIANT");
     const int v = e ? atoi(e) : 0;
     if (sizeof(T) == 4 && OP == OP_PULL && (ORDER == 3 || ORDER == 1)) {
         switch (v) {
-        case 1: return launch_pull_tile_cfg<T, ORDER, OP, 8, 8, 32, 256, 2>(kp, vol, grid, out, stream, 84 * 1024);
-        case 2: return launch_pull_tile_cfg<T, ORDER, OP, 8, 4, 32, 128, 4>(kp, vol, grid, out, stream, 56 * 1024);
-        case 3: return launch_pull_tile_cfg<T, ORDER, OP, 8, 4, 32, 128, 5>(kp, vol, grid, out, stream, 44 * 1024);
-        case 4: return launch_pull_tile_cfg<T, ORDER, OP, 4, 8, 32, 256, 3>(kp, vol, grid, out, stream, 56 * 1024);
-        case 5: return launch_pull_tile_cfg<T, ORDER, OP, 4, 4, 32, 128, 6>(kp, vol, grid, out, stream, 36 * 1024);
+        case 1: return launch_pull_tile_cfg<T, ORDER, OP, 8, 8, 32, 256, 2>(kp, vol, grid, gout, out, stream, 84 * 1024);
+        case 2: return launch_pull_tile_cfg<T, ORDER, OP, 8, 4, 32, 128, 4>(kp, vol, grid, gout, out, stream, 56 * 1024);
+        case 3: return launch_pull_tile_cfg<T, ORDER, OP, 8, 4, 32, 128, 5>(kp, vol, grid, gout, out, stream, 44 * 1024);
+        case 4: return launch_pull_tile_cfg<T, ORDER, OP, 4, 8, 32, 256, 3>(kp, vol, grid, gout, out, stream, 56 * 1024);
+        case 5: return launch_pull_tile_cfg<T, ORDER, OP, 4, 4, 32, 128, 6>(kp, vol, grid, gout, out, stream, 36 * 1024);
         }
     }
 #endif
-    return launch_pull_tile_cfg<T, ORDER, OP, 8, 8, 32, 256, 2>(kp, vol, grid, out, stream, 110 * 1024);
+    return launch_pull_tile_cfg<T, ORDER, OP, 8, 8, 32, 256, 2>(kp, vol, grid, gout, out, stream, 110 * 1024);
 }
 
 template <typename T, int OP>
-static int dispatch_pull_tile(const KParams &kp, const void *vol, const void *grid, void *out, cudaStream_t stream) {
+static int dispatch_pull_tile(const KParams &kp, const void *vol, const void *grid, const void *gout, void *out, cudaStream_t stream) {
     switch (kp.order[0]) {
-    case 1: return launch_pull_tile<T, 1, OP>(kp, vol, grid, out, stream);
-    case 2: return launch_pull_tile<T, 2, OP>(kp, vol, grid, out, stream);
-    case 3: return launch_pull_tile<T, 3, OP>(kp, vol, grid, out, stream);
-    case 4: return launch_pull_tile<T, 4, OP>(kp, vol, grid, out, stream);
-    case 5: return launch_pull_tile<T, 5, OP>(kp, vol, grid, out, stream);
-    case 6: return launch_pull_tile<T, 6, OP>(kp, vol, grid, out, stream);
-    case 7: return launch_pull_tile<T, 7, OP>(kp, vol, grid, out, stream);
+    case 1: return launch_pull_tile<T, 1, OP>(kp, vol, grid, gout, out, stream);
+    case 2: return launch_pull_tile<T, 2, OP>(kp, vol, grid, gout, out, stream);
+    case 3: return launch_pull_tile<T, 3, OP>(kp, vol, grid, gout, out, stream);
+    case 4: return launch_pull_tile<T, 4, OP>(kp, vol, grid, gout, out, stream);
+    case 5: return launch_pull_tile<T, 5, OP>(kp, vol, grid, gout, out, stream);
+    case 6: return launch_pull_tile<T, 6, OP>(kp, vol, grid, gout, out, stream);
+    case 7: return launch_pull_tile<T, 7, OP>(kp, vol, grid, gout, out, stream);
     }
     return 0;
 }
 
-int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const void *grid, void *out, cudaStream_t stream) {
-    if (op != OP_PULL && op != OP_GRAD) return 0;
+int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const void *grid, const void *gout, void *out,
+                   cudaStream_t stream) {
+    if (op != OP_PULL && op != OP_GRAD && op != OP_PULL_BWD_GRID) return 0;
     if (kp.dim != 3 || !kp.pts_dense) return 0;
     if (kp.order[0] != kp.order[1] || kp.order[0] != kp.order[2]) return 0;
     if (kp.pts_total < 32768) return 0;                        // small problems: one generic launch
@@ -273,14 +288,17 @@ int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const 
     if (kp.flags & IB200_FLAG_REF_LINEAR_GRAD_SIGN) return 0;
     if (op == OP_PULL) {
         switch (dtype) {
-        case IB200_F32: return dispatch_pull_tile<float, OP_PULL>(kp, vol, grid, out, stream);
-        case IB200_F16: return dispatch_pull_tile<__half, OP_PULL>(kp, vol, grid, out, stream);
+        case IB200_F32: return dispatch_pull_tile<float, OP_PULL>(kp, vol, grid, nullptr, out, stream);
+        case IB200_F16: return dispatch_pull_tile<__half, OP_PULL>(kp, vol, grid, nullptr, out, stream);
         }
-    } else {
+    } else if (op == OP_GRAD) {
         switch (dtype) {
-        case IB200_F32: return dispatch_pull_tile<float, OP_GRAD>(kp, vol, grid, out, stream);
-        case IB200_F16: return dispatch_pull_tile<__half, OP_GRAD>(kp, vol, grid, out, stream);
+        case IB200_F32: return dispatch_pull_tile<float, OP_GRAD>(kp, vol, grid, nullptr, out, stream);
+        case IB200_F16: return dispatch_pull_tile<__half, OP_GRAD>(kp, vol, grid, nullptr, out, stream);
         }
+    } else if (dtype == IB200_F32 && gout && kp.channels >= 1) {
+        // (16-bit storage would round the running sum once per channel: the generic kernel sums in registers)
+        return dispatch_pull_tile<float, OP_PULL_BWD_GRID>(kp, vol, grid, gout, out, stream);
     }
     return 0;
 }

@@ -58,6 +58,7 @@ def lib():
         for name in ('ib200_pull', 'ib200_grad', 'ib200_hess', 'ib200_pull_labels'):
             getattr(L, name).argtypes = [pp, vp, vp, vp, vp]
         L.ib200_pull_backward_grid.argtypes = [pp, vp, vp, vp, vp, vp]
+        L.ib200_grad_backward_grid.argtypes = [pp, vp, vp, vp, vp, vp]
         L.ib200_push.argtypes = [pp, vp, vp, vp, vp, vp]
         L.ib200_pushgrad.argtypes = [pp, vp, vp, vp, vp, vp]
         L.ib200_count.argtypes = [pp, vp, vp, vp, vp]
@@ -72,7 +73,7 @@ def lib():
         L.ib200_error_string.restype = ctypes.c_char_p
         L.ib200_last_kernel.restype = ctypes.c_char_p
         L.ib200_launch_count.restype = ctypes.c_uint64
-        for name in ('ib200_pull', 'ib200_grad', 'ib200_hess', 'ib200_pull_backward_grid', 'ib200_push',
+        for name in ('ib200_pull', 'ib200_grad', 'ib200_hess', 'ib200_pull_backward_grid', 'ib200_grad_backward_grid', 'ib200_push',
                      'ib200_pushgrad', 'ib200_count', 'ib200_spline_coeff', 'ib200_abi_version', 'ib200_pull_labels'):
             getattr(L, name).restype = ctypes.c_int
         if L.ib200_abi_version() != 1:

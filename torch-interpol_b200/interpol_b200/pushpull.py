@@ -108,7 +108,7 @@ def _batch(*tensors):
     return b
 
 
-def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gout=None):
+def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gout=None, gout_comp=False):
     _lib.require_cuda(inp, grid, gout)
     dim = grid.shape[-1]
     if grid.dim() != dim + 2 or inp.dim() != dim + 2:
@@ -132,10 +132,10 @@ def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gou
             st = getattr(L, fn_name)(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid), _lib.ptr(out), s)
         else:
             gout = gout.to(dtype)
-            _set_img(p, gout, batch, dim)
+            _set_img(p, gout, batch, dim, comp=gout_comp)
             out = torch.empty([batch, *oshape, dim], dtype=dtype, device=grid.device)
-            st = L.ib200_pull_backward_grid(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid),
-                                            _lib.ptr(gout), _lib.ptr(out), s)
+            fn = L.ib200_grad_backward_grid if gout_comp else L.ib200_pull_backward_grid
+            st = fn(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid), _lib.ptr(gout), _lib.ptr(out), s)
     _lib.check(st)
     return out
 
@@ -184,6 +184,12 @@ def grid_pull_grad_grid(gout, inp, grid, bound, interpolation, extrapolate):
     """Fused `(grid_grad(inp, grid) * gout.unsqueeze(-1)).sum(1)` -> (B, *spatial_out, D)
     (the grid branch of interpol/pushpull.py:254-257 without the (B,C,*,D) temporary)."""
     return _gather('', inp, grid, bound, interpolation, extrapolate, None, gout=gout)
+
+
+def grid_grad_grad_grid(gout, inp, grid, bound, interpolation, extrapolate):
+    """Fused `(grid_hess(inp, grid) * gout.unsqueeze(-1)).sum(dim=[1, -2])` -> (B, *spatial_out, D), gout
+    (B, C, *spatial_out, D): the grid branch of interpol/pushpull.py:318-324 without the (B,C,*,D,D) Hessian."""
+    return _gather('', inp, grid, bound, interpolation, extrapolate, None, gout=gout, gout_comp=True)
 
 
 def _scatter(fn_name, inp, grid, shape, bound, interpolation, extrapolate, comp=False):
@@ -278,6 +284,9 @@ def grid_push_backward(grad, inp, grid, bound, interpolation, extrapolate):
 
 def grid_count_backward(grad, grid, bound, interpolation, extrapolate):
     """-> (B, *spatial_in, D).  Reference: pushpull.py:286-299."""
+    if grid.requires_grad and grad.shape[1] == 1:
+        # one channel (what GridCount produces): the gradient kernels' own fast paths
+        return grid_grad(grad, grid, bound, interpolation, extrapolate)[:, 0]
     if grid.requires_grad:
         ones = torch.ones([1, 1, *([1] * (grid.dim() - 2))], dtype=grad.dtype, device=grad.device)
         ones = ones.expand([grid.shape[0], grad.shape[1], *grid.shape[1:-1]])
@@ -294,6 +303,5 @@ def grid_grad_backward(grad, inp, grid, bound, interpolation, extrapolate):
     if inp.requires_grad:
         grad_inp = grid_pushgrad(grad, grid, shape, bound, interpolation, extrapolate)
     if grid.requires_grad:
-        hess = grid_hess(inp, grid, bound, interpolation, extrapolate)
-        grad_grid = (hess * grad.unsqueeze(-1)).sum(dim=[1, -2])
+        grad_grid = grid_grad_grad_grid(grad, inp, grid, bound, interpolation, extrapolate)
     return grad_inp, grad_grid

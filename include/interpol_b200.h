@@ -82,7 +82,11 @@ enum {
      * tiled kernels; A/B testing, profiling) */
     IB200_FLAG_NO_PIPE = 1u << 2,
     /* take the persistent kernels even for problems too small to amortise their ramp-up (tests) */
-    IB200_FLAG_FORCE_PIPE = 1u << 3
+    IB200_FLAG_FORCE_PIPE = 1u << 3,
+    /* `grid` holds DISPLACEMENTS in voxels: the sampling coordinate of lattice point x is x + grid[x]
+     * (what interpol.add_identity_grid builds, api.py:482-520, formed in registers instead: the identity
+     * grid is never read or written).  Results equal add_identity_grid + the same call. */
+    IB200_FLAG_DISPLACEMENT = 1u << 4
 };
 
 /*

@@ -430,3 +430,47 @@ def test_label_pull_fused_matches_label_loop(dim):
     finally:
         api.LABELS_FUSED = True
     assert torch.equal(a, b)
+
+
+def test_real_reference_forwards_through_the_seam():
+    """The UNMODIFIED reference (baseline/_ref) with this engine installed through its own plugin seam
+    (interpol/backend.py:1 + interpol/api.py:186-441): `interpol.grid_pull(...)` on CUDA tensors must run
+    this repo's kernels (launch counter advances, kernel names are ours) and return what the reference's own
+    TorchScript path returns on the CPU for the same inputs."""
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_dir = os.path.join(root, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'interpol')):
+        pytest.skip('baseline/_ref not present')
+    sys.path.insert(0, ref_dir)
+    import warnings
+    warnings.filterwarnings('ignore')
+    try:
+        import interpol as ref
+    finally:
+        sys.path.remove(ref_dir)
+    import interpol_b200 as ib
+    gen = torch.Generator().manual_seed(31)
+    shape = (40, 36, 44)
+    vol = torch.randn([1, 2, *shape], generator=gen)
+    grid = smooth_grid(shape, gen)           # (component-major strides: densified on the way in)
+    kw = dict(interpolation=3, bound='dct2', extrapolate=True)
+    want = {fn: getattr(ref, fn)(vol.double(), grid.double(), **kw) for fn in ('grid_pull', 'grid_grad', 'grid_push')}
+    want['grid_count'] = ref.grid_count(grid.double(), **kw)
+    want['coeff'] = ref.spline_coeff_nd(vol.double(), interpolation=3, bound='dct2', dim=3)
+    assert ref.backend.jitfields is False
+    ib.install_as_backend(ref)
+    try:
+        assert ref.backend.jitfields is True and ref.api.jitfields.available
+        n0 = ib.launch_count()
+        got = {fn: getattr(ref, fn)(vol.cuda(), grid.cuda(), **kw) for fn in ('grid_pull', 'grid_grad', 'grid_push')}
+        assert ib.last_kernel().startswith(('push_box3d', 'push_tile3d')), ib.last_kernel()
+        got['grid_count'] = ref.grid_count(grid.cuda(), **kw)
+        got['coeff'] = ref.spline_coeff_nd(vol.cuda(), interpolation=3, bound='dct2', dim=3)
+        assert ib.last_kernel().startswith('coeff_'), ib.last_kernel()
+        assert ib.launch_count() - n0 >= 7                       # pull, grad, push, count, 3 prefilter passes
+        for k in want:
+            assert got[k].is_cuda
+            assert rel_err(to_np(got[k]), want[k].numpy()) <= 1e-5, k
+    finally:
+        ref.backend.jitfields = False

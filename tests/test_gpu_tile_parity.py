@@ -333,3 +333,45 @@ def test_fused_backward_full_size():
     assert rel_err(to_np(v.grad), to_np(ref_gi)) <= 1e-6
     want = oracle.grid_grad(to_np(vol), to_np(grid), [3], [3], 1)[:, 0] * to_np(gout)[0, 0, ..., None]
     assert rel_err(to_np(g.grad), want) <= 1e-5
+
+
+# --------------------------------------------------------- displacement fields --
+
+@pytest.mark.parametrize('dim,shape', [(1, (300,)), (2, (48, 40)), (3, (20, 24, 18)), (3, SHAPE)])
+def test_displacement_mode_equals_identity_plus_grid(dim, shape):
+    """`displacement=True` (IB200_FLAG_DISPLACEMENT: coordinate = lattice index + grid value, formed in registers)
+    returns what add_identity_grid + the same call returns (interpol/api.py:482-520), for every op, the generic
+    and the tiled kernels, float32 and float16, and through autograd."""
+    import interpol_b200 as ib
+    gen = torch.Generator().manual_seed(60 + dim + len(shape) * shape[0])
+    B, C = 2, 2
+    vol = torch.randn([B, C, *shape], generator=gen).cuda()
+    disp = (smooth_grid(shape, gen, amp=3.0, batch=B) - ib.identity_grid(shape)).contiguous().cuda()
+    grid = ib.add_identity_grid(disp)
+    for order, bound, ex in ((3, 'dct2', True), (1, 'zero', False), (2, 'dft', 2)):
+        kw = dict(interpolation=order, bound=bound, extrapolate=ex)
+        for fn in (ib.grid_pull, ib.grid_grad, ib.grid_push):
+            a = fn(vol, disp, displacement=True, **kw)
+            b = fn(vol, grid, **kw)
+            assert rel_err(to_np(a), to_np(b)) <= 2e-6, (fn.__name__, order, bound)
+        a = ib.grid_count(disp, displacement=True, **kw)
+        b = ib.grid_count(grid, **kw)
+        assert rel_err(to_np(a), to_np(b)) <= 2e-6
+    if dim == 3:
+        # float16 storage: the lattice index is added in float32 (more accurate than a materialised float16 grid)
+        h = ib.grid_pull(vol.half(), disp.half(), interpolation=3, bound='dct2', extrapolate=True, displacement=True)
+        assert h.dtype == torch.float16
+        want = ib.grid_pull(vol.half().float(), ib.add_identity_grid(disp.half().float()), interpolation=3, bound='dct2',
+                            extrapolate=True)
+        assert rel_err(to_np(h), to_np(want)) <= 2e-3
+        lab = torch.randint(0, 5, [B, 1, *shape], generator=gen).cuda()
+        assert torch.equal(ib.grid_pull(lab, disp, interpolation=1, bound='dct2', extrapolate=True, displacement=True),
+                           ib.grid_pull(lab, grid, interpolation=1, bound='dct2', extrapolate=True))
+    # autograd: d/d(displacement) == d/d(coordinate)
+    v1 = vol.clone().requires_grad_(); d1 = disp.clone().requires_grad_()
+    v2 = vol.clone().requires_grad_(); g2 = grid.clone().requires_grad_()
+    gout = torch.randn(vol.shape[:2] + tuple(shape), generator=gen).cuda()
+    ib.grid_pull(v1, d1, interpolation=3, bound='dct2', extrapolate=True, displacement=True).backward(gout)
+    ib.grid_pull(v2, g2, interpolation=3, bound='dct2', extrapolate=True).backward(gout)
+    assert rel_err(to_np(v1.grad), to_np(v2.grad)) <= 2e-6
+    assert rel_err(to_np(d1.grad), to_np(g2.grad)) <= 2e-6

@@ -62,6 +62,8 @@ static int build_params(const ib200_problem *p, int need, KParams &kp) {
         if (p->order[d] < 0 || p->order[d] > 7) return IB200_ERR_ORDER;
         if (p->vol_shape[d] < 1 || p->pts_shape[d] < 0) return IB200_ERR_SHAPE;
         if (p->vol_shape[d] > 0x7fffffffLL || p->pts_shape[d] > 0x7fffffffLL) return IB200_ERR_TOO_LARGE;
+        // the boundary maps fold with 2 * n and 2 * (n + 1) in 32-bit arithmetic (support.cuh)
+        if (p->vol_shape[d] > 0x3fffffffLL) return IB200_ERR_TOO_LARGE;
         kp.bound[d] = p->bound[d];
         kp.order[d] = p->order[d];
         kp.vol_n[d] = (int)p->vol_shape[d];
@@ -289,7 +291,7 @@ static int resample_common(int adjoint, const void *in, void *out, const void *c
     if (order < 0 || order > 7) return IB200_ERR_ORDER;
     if (extrapolate < 0 || extrapolate > 2) return IB200_ERR_EXTRAPOLATE;
     if (outer < 0 || n_vol < 1 || n_pts < 0 || inner < 0) return IB200_ERR_SHAPE;
-    if (n_vol > 0x7fffffffLL || n_pts > 0x7fffffffLL || n_vol * inner > 0x7fffffffLL) return IB200_ERR_TOO_LARGE;
+    if (n_vol > 0x3fffffffLL || n_pts > 0x7fffffffLL || n_vol * inner > 0x7fffffffLL) return IB200_ERR_TOO_LARGE;
     if (outer * n_dst * inner == 0) return IB200_OK;
     if (!out || (outer * n_pts * inner != 0 && (!in || !coords))) return IB200_ERR_NULL;
     KParams kp;
@@ -335,7 +337,7 @@ const char *ib200_error_string(int status) {
     case IB200_ERR_BOUND_UNSUPPORTED: return "boundary condition not implemented for the spline prefilter";
     case IB200_ERR_SCRATCH: return "16-bit scatter needs a float32 scratch volume";
     case IB200_ERR_EXTRAPOLATE: return "extrapolate must be 0, 1 or 2";
-    case IB200_ERR_TOO_LARGE: return "a single volume must have fewer than 2^31 voxels";
+    case IB200_ERR_TOO_LARGE: return "a single volume must have fewer than 2^31 voxels (and fewer than 2^30 along one axis)";
     }
     if (status <= IB200_ERR_CUDA) return cudaGetErrorString((cudaError_t)(IB200_ERR_CUDA - status));
     return "unknown error";

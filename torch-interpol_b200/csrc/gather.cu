@@ -50,11 +50,13 @@ gather_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
          p += (i64)gridDim.x * blockDim.x) {
         i64 b; int xyz[3];
         i64 goff, ioff;   // offsets of this point in the grid / in a lattice image
+        const bool disp = (kp.flags & IB200_FLAG_DISPLACEMENT) != 0;
         if (kp.pts_dense) {
             b = p / kp.pts_total;
             const i64 r = p - b * kp.pts_total;
             goff = b * kp.grid_sb + r * DIM;
             ioff = r;
+            if (disp) decompose<DIM>(kp, p, b, xyz);
         } else {
             decompose<DIM>(kp, p, b, xyz);
             goff = b * kp.grid_sb; ioff = 0;
@@ -65,7 +67,7 @@ gather_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
 
         R coord[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) coord[d] = Traits<T>::load(grid + goff + d * kp.grid_sd);
+        for (int d = 0; d < DIM; ++d) coord[d] = Traits<T>::load(grid + goff + d * kp.grid_sd) + (disp ? (R)xyz[d] : R(0));
 
         bool ok = inbounds<R, DIM>(kp, coord);
         Axis<R, NODES> ax[3];

@@ -21,9 +21,15 @@ pull_labels_kernel(const __grid_constant__ KParams kp, const int *__restrict__ v
     for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (i64)gridDim.x * blockDim.x) {
         i64 b; int xyz[3];
         i64 goff;
+        const bool disp = (kp.flags & IB200_FLAG_DISPLACEMENT) != 0;
         if (kp.pts_dense) {
             b = p / kp.pts_total;
             goff = b * kp.grid_sb + (p - b * kp.pts_total) * DIM;
+            if (disp) {
+                i64 r = p;
+#pragma unroll
+                for (int d = DIM - 1; d >= 0; --d) { xyz[d] = (int)(r % kp.pts_n[d]); r /= kp.pts_n[d]; }
+            }
         } else {
             i64 r = p;
             goff = 0;
@@ -35,7 +41,7 @@ pull_labels_kernel(const __grid_constant__ KParams kp, const int *__restrict__ v
         const i64 r_dense = p - b * kp.pts_total;
         R coord[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) coord[d] = Traits<G>::load(grid + goff + d * kp.grid_sd);
+        for (int d = 0; d < DIM; ++d) coord[d] = Traits<G>::load(grid + goff + d * kp.grid_sd) + (disp ? (R)xyz[d] : R(0));
         bool ok = inbounds<R, DIM>(kp, coord);
         Axis<R, 8> ax[3];
 #pragma unroll

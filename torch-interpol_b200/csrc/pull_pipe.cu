@@ -496,7 +496,7 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
     if (kp.order[0] < 1 || kp.order[0] > 3) return 0;
     if (kp.pts_total < 32768) return 0;
     if (kp.pts_total * 3 > 0x7fffffffLL) return 0;
-    if (kp.flags & (IB200_FLAG_REF_LINEAR_GRAD_SIGN | IB200_FLAG_NO_PIPE)) return 0;
+    if (kp.flags & (IB200_FLAG_REF_LINEAR_GRAD_SIGN | IB200_FLAG_NO_PIPE | IB200_FLAG_DISPLACEMENT)) return 0;   // (displacement fields: tile kernel)
     // The pipeline needs a dozen tiles per CTA to amortise its ramp-up (128^3: 7 per CTA, 0.20 ms against
     // 0.10 ms for the one-tile-per-CTA kernel), and with several channels the tile kernel, which shares one
     // plan and one staged grid tile between the channels of a tile, is still 3-7 % ahead (256^3 C=4: pull 1.13

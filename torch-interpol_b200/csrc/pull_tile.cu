@@ -67,6 +67,7 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
     stage_grid_tile<T, TX, TY, TZ, NT>(kp, grid + b * kp.grid_sb, gtile, x0, y0, z0, nzv, vec_ok);
     cp_async_wait_all();
     __syncthreads();
+    tile_add_identity<T, TX, NT>(kp, gtile, x0, y0 + ly, z0 + lz);
     plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap, 0.f, TZ == 16 ? 16 : 32);
     const int nsub = *nsub_p;
     const int per = TX / nsub;
@@ -286,6 +287,8 @@ int try_pull_tiled(int op, const KParams &kp, int dtype, const void *vol, const 
     if (kp.pts_total * 3 > 0x7fffffffLL) return 0;             // 32-bit offsets inside one batch element
     if (kp.vol_s[2] != 1) return 0;                            // staging wants a unit innermost stride
     if (kp.flags & IB200_FLAG_REF_LINEAR_GRAD_SIGN) return 0;
+    // displacement fields in 16-bit storage: the generic kernels add the lattice index in float32
+    if ((kp.flags & IB200_FLAG_DISPLACEMENT) && dtype != IB200_F32) return 0;
     if (op == OP_PULL) {
         switch (dtype) {
         case IB200_F32: return dispatch_pull_tile<float, OP_PULL>(kp, vol, grid, nullptr, out, stream);

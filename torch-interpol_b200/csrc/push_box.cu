@@ -150,6 +150,7 @@ push_box3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ CU
     unsigned vphase = 0;                   // parity of the value barrier
     bool dirty = false;                    // (block-uniform) the box holds flushed sums / a flush may still be running
     mbar_wait(bar, 0);
+    tile_add_identity<T, TX, NT>(kp, gtile, x0, y0 + ly, z0 + lz);
     if (!COUNT) { mbar_wait(bar + 1, 0); ++vphase; }
 
     // ---- 2. front end: ONE pass over the tile's coordinates and values -------------------

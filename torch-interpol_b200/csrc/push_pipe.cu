@@ -565,7 +565,7 @@ int try_push_pipe(int op, const KParams &kp, int dtype, const void *img, const v
     if (kp.order[0] < 1 || kp.order[0] > 3) return 0;
     if (kp.pts_total < 32768) return 0;
     if (kp.pts_total * 3 > 0x7fffffffLL) return 0;
-    if (kp.flags & IB200_FLAG_NO_PIPE) return 0;
+    if (kp.flags & (IB200_FLAG_NO_PIPE | IB200_FLAG_DISPLACEMENT)) return 0;
     // Not the default: both scatter kernels are bound by the shared-memory atomic pipe (64 ATOMS per source at
     // ~2.7 clk each once same-bank / same-address lanes serialise), and on the 256^3 cubic workload the
     // one-tile-per-CTA kernel (0.67 ms) still beats this one (0.73 ms) -- see DESIGN.md.  IB200_FLAG_FORCE_PIPE selects it.

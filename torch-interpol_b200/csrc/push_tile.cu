@@ -93,6 +93,7 @@ push_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img
     stage_values(0);
     cp_async_wait_all();
     __syncthreads();
+    tile_add_identity<T, TX, NT>(kp, gtile, x0, y0 + ly, z0 + lz);
     plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap, local_vmax());
     float vmax_tile = __int_as_float(red[kExtraSlot]);
     i64 cur_c = 0;                         // channel whose values are staged in `vals`
@@ -329,6 +330,8 @@ bool push_tiled_applicable(int op, const KParams &kp, int dtype) {
     if (kp.order[0] < 1 || kp.order[0] > 7) return false;
     if (kp.pts_total < 32768) return false;
     if (kp.pts_total * 3 > 0x7fffffffLL) return false;
+    // displacement fields in 16-bit storage: the generic kernels add the lattice index in float32
+    if ((kp.flags & IB200_FLAG_DISPLACEMENT) && dtype != IB200_F32) return false;
     return true;
 }
 

@@ -36,13 +36,10 @@ scatter_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img,
          p += (i64)gridDim.x * blockDim.x) {
         i64 b = p / kp.pts_total;
         i64 goff, ioff;
-        if (kp.pts_dense) {
-            const i64 r = p - b * kp.pts_total;
-            goff = b * kp.grid_sb + r * DIM;
-            ioff = r * (OP == OP_PUSHGRAD ? DIM : 1);
-        } else {
-            i64 r = p - b * kp.pts_total;
-            int xyz[3] = {0, 0, 0};
+        const bool disp = (kp.flags & IB200_FLAG_DISPLACEMENT) != 0;
+        int xyz[3] = {0, 0, 0};
+        if (!kp.pts_dense || disp) {
+            i64 r = p - (p / kp.pts_total) * kp.pts_total;
             if (DIM == 3) {
                 const i64 yz = (i64)kp.pts_n[1] * kp.pts_n[2];
                 xyz[0] = (int)(r / yz); r -= (i64)xyz[0] * yz;
@@ -52,6 +49,14 @@ scatter_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img,
             } else {
                 xyz[0] = (int)r;
             }
+        }
+        if (kp.pts_dense) {
+            b = p / kp.pts_total;
+            const i64 r = p - b * kp.pts_total;
+            goff = b * kp.grid_sb + r * DIM;
+            ioff = r * (OP == OP_PUSHGRAD ? DIM : 1);
+        } else {
+            b = p / kp.pts_total;
             goff = b * kp.grid_sb; ioff = 0;
 #pragma unroll
             for (int d = 0; d < DIM; ++d) { goff += xyz[d] * kp.grid_s[d]; ioff += xyz[d] * kp.img_s[d]; }
@@ -59,7 +64,7 @@ scatter_kernel(const __grid_constant__ KParams kp, const T *__restrict__ img,
 
         R coord[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) coord[d] = Traits<T>::load(grid + goff + d * kp.grid_sd);
+        for (int d = 0; d < DIM; ++d) coord[d] = Traits<T>::load(grid + goff + d * kp.grid_sd) + (disp ? (R)xyz[d] : R(0));
 
         bool ok = inbounds<R, DIM>(kp, coord);      // nd.py:201-203: masked sources add nothing
         Axis<R, NODES> ax[3];

@@ -187,6 +187,21 @@ __device__ __forceinline__ void stage_grid_tile(const KParams &kp, const T *grid
     }
 }
 
+// Displacement fields (IB200_FLAG_DISPLACEMENT): the staged tile holds displacements; every thread turns ITS OWN
+// points (plane p, column threadIdx.x -- the only ones it ever reads) into coordinates, in place.  (float32
+// tiles only: 16-bit displacement fields take the generic kernels, which add the index in float32.)
+template <typename T, int TX, int NT>
+__device__ __forceinline__ void tile_add_identity(const KParams &kp, T *gtile, int x0, int y, int z) {
+    if (!(kp.flags & IB200_FLAG_DISPLACEMENT)) return;
+#pragma unroll
+    for (int p = 0; p < TX; ++p) {
+        T *g = gtile + (p * NT + threadIdx.x) * 3;
+        g[0] = (T)((float)g[0] + (float)(x0 + p));
+        g[1] = (T)((float)g[1] + (float)y);
+        g[2] = (T)((float)g[2] + (float)z);
+    }
+}
+
 // support start of the point of this thread in plane p: 0 inactive, 1 ok, 2 absurd
 template <typename T, int ORDER, int NT>
 __device__ __forceinline__ int support_start(const KParams &kp, const T *gtile, int p, bool in_tile, int (&i0)[3]) {

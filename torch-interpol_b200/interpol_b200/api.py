@@ -254,13 +254,17 @@ def _labels_fused_ok(input, grid, interpolation):
 # --------------------------------------------------------------------------
 
 def grid_pull(input, grid, interpolation='linear', bound='zero',
-              extrapolate=False, prefilter=False):
+              extrapolate=False, prefilter=False, *, displacement=False):
     """Sample an image with respect to a deformation field.
 
     input : (..., [channel], *inshape) tensor;  grid : (..., *outshape, dim) tensor
     interpolation : int | str | list, default 'linear' (orders 0..7)
     bound : str | int | list, default 'zero' (zero, replicate, dct1, dct2, dst1, dst2, dft)
     extrapolate : bool | int, default False;  prefilter : bool, default False
+    displacement : bool, default False (extension, keyword only; also on grid_push / grid_count / grid_grad):
+        `grid` holds displacements in voxels -- the coordinate of lattice point x is x + grid[x], formed in
+        registers: same result as `grid_pull(input, add_identity_grid(grid), ...)` (api.py:482-520) without
+        reading or writing the identity grid
     returns (..., [channel], *outshape)
 
     Integer inputs are treated as label maps: every label is resampled as a
@@ -276,7 +280,7 @@ def grid_pull(input, grid, interpolation='linear', bound='zero',
         from .autograd import _options
         from . import pushpull as _pp
         bnd, order, extr = _options(interpolation, bound, extrapolate)
-        out = _pp.grid_pull_labels(input.to(torch.int32), grid, bnd, order, extr).to(input.dtype)
+        out = _pp.grid_pull_labels(input.to(torch.int32), grid, bnd, order, extr, displacement).to(input.dtype)
     elif not input.dtype.is_floating_point:
         out = input.new_zeros([batch, channel, *grid.shape[1:-1]])
         pmax = grid.new_zeros([batch, channel, *grid.shape[1:-1]])
@@ -285,20 +289,20 @@ def grid_pull(input, grid, interpolation='linear', bound='zero',
             if prefilter:
                 soft = spline_coeff_nd(soft, interpolation=interpolation,
                                        bound=bound, dim=dim, inplace=True)
-            soft = GridPull.apply(soft, grid, interpolation, bound, extrapolate)
+            soft = GridPull.apply(soft, grid, interpolation, bound, extrapolate, displacement)
             out[soft > pmax] = label
             pmax = torch.max(pmax, soft)
     else:
         if prefilter:
             input = spline_coeff_nd(input, interpolation=interpolation,
                                     bound=bound, dim=dim)
-        out = GridPull.apply(input, grid, interpolation, bound, extrapolate)
+        out = GridPull.apply(input, grid, interpolation, bound, extrapolate, displacement)
 
     return back(_postproc(out, shape_info, mode='pull'))
 
 
 def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
-              extrapolate=False, prefilter=False):
+              extrapolate=False, prefilter=False, *, displacement=False):
     """Splat an image with respect to a deformation field (adjoint of pull).
 
     input : (..., [channel], *inshape);  grid : (..., *inshape, dim)
@@ -312,7 +316,7 @@ def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
     if shape is None:
         shape = tuple(input.shape[2:])
 
-    out = GridPush.apply(input, grid, shape, interpolation, bound, extrapolate)
+    out = GridPush.apply(input, grid, shape, interpolation, bound, extrapolate, displacement)
     if prefilter:
         out = spline_coeff_nd(out, interpolation=interpolation, bound=bound,
                               dim=dim, inplace=True)
@@ -320,19 +324,19 @@ def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
 
 
 def grid_count(grid, shape=None, interpolation='linear', bound='zero',
-               extrapolate=False):
+               extrapolate=False, *, displacement=False):
     """Splatting weights of a deformation field (push of an image of ones).
 
     grid : (..., *inshape, dim);  returns (..., [1], *shape)   (reference: api.py:265-299)
     """
     (grid,), back = _stage(grid)
     grid, shape_info = _preproc(grid)
-    out = GridCount.apply(grid, shape, interpolation, bound, extrapolate)
+    out = GridCount.apply(grid, shape, interpolation, bound, extrapolate, displacement)
     return back(_postproc(out, shape_info, mode='count'))
 
 
 def grid_grad(input, grid, interpolation='linear', bound='zero',
-              extrapolate=False, prefilter=False):
+              extrapolate=False, prefilter=False, *, displacement=False):
     """Sample the spatial gradients of an image with respect to a deformation field.
 
     returns (..., [channel], *outshape, dim)                  (reference: api.py:302-344)
@@ -342,7 +346,7 @@ def grid_grad(input, grid, interpolation='linear', bound='zero',
     dim = grid.shape[-1]
     if prefilter:
         input = spline_coeff_nd(input, interpolation, bound, dim)
-    out = GridGrad.apply(input, grid, interpolation, bound, extrapolate)
+    out = GridGrad.apply(input, grid, interpolation, bound, extrapolate, displacement)
     return back(_postproc(out, shape_info, mode='grad'))
 
 

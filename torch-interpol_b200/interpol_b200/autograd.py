@@ -102,8 +102,9 @@ class GridPull(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, input, grid, interpolation, bound, extrapolate):
-        opt = _options(interpolation, bound, extrapolate)
+    def forward(ctx, input, grid, interpolation, bound, extrapolate, displacement=False):
+        # (`displacement`: optional sixth argument, an extension -- the grid holds displacements)
+        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
         output = grid_pull(input, grid, *opt)
         ctx.opt = opt
         ctx.save_for_backward(input, grid)
@@ -113,7 +114,7 @@ class GridPull(torch.autograd.Function):
     @custom_bwd(device_type='cuda')
     def backward(ctx, grad):
         grad_input, grad_grid = grid_pull_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_input, grad_grid, None, None, None
+        return grad_input, grad_grid, None, None, None, None
 
 
 class GridPush(torch.autograd.Function):
@@ -121,8 +122,8 @@ class GridPush(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, input, grid, shape, interpolation, bound, extrapolate):
-        opt = _options(interpolation, bound, extrapolate)
+    def forward(ctx, input, grid, shape, interpolation, bound, extrapolate, displacement=False):
+        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
         output = grid_push(input, grid, shape, *opt)
         ctx.opt = opt
         ctx.save_for_backward(input, grid)
@@ -132,7 +133,7 @@ class GridPush(torch.autograd.Function):
     @custom_bwd(device_type='cuda')
     def backward(ctx, grad):
         grad_input, grad_grid = grid_push_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_input, grad_grid, None, None, None, None
+        return grad_input, grad_grid, None, None, None, None, None
 
 
 class GridCount(torch.autograd.Function):
@@ -140,8 +141,8 @@ class GridCount(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, grid, shape, interpolation, bound, extrapolate):
-        opt = _options(interpolation, bound, extrapolate)
+    def forward(ctx, grid, shape, interpolation, bound, extrapolate, displacement=False):
+        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
         output = grid_count(grid, shape, *opt)
         ctx.opt = opt
         ctx.save_for_backward(grid)
@@ -153,7 +154,7 @@ class GridCount(torch.autograd.Function):
         grad_grid = None
         if ctx.needs_input_grad[0]:
             grad_grid = grid_count_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_grid, None, None, None, None
+        return grad_grid, None, None, None, None, None
 
 
 class GridGrad(torch.autograd.Function):
@@ -161,8 +162,8 @@ class GridGrad(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, input, grid, interpolation, bound, extrapolate):
-        opt = _options(interpolation, bound, extrapolate)
+    def forward(ctx, input, grid, interpolation, bound, extrapolate, displacement=False):
+        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
         output = grid_grad(input, grid, *opt)
         ctx.opt = opt
         ctx.save_for_backward(input, grid)
@@ -174,7 +175,7 @@ class GridGrad(torch.autograd.Function):
         grad_input = grad_grid = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             grad_input, grad_grid = grid_grad_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_input, grad_grid, None, None, None
+        return grad_input, grad_grid, None, None, None, None
 
 
 class SplineCoeff(torch.autograd.Function):

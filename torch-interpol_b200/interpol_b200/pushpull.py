@@ -45,8 +45,11 @@ def _common_dtype(*tensors):
     return dt
 
 
+DISPLACEMENT = 16     # IB200_FLAG_DISPLACEMENT: the grid holds displacements (coordinate = lattice index + value)
+
+
 def _problem(dim, dtype, device, bound, interpolation, extrapolate, batch, channels,
-             vol_shape, pts_shape):
+             vol_shape, pts_shape, displacement=False):
     if dim < 1 or dim > 3:
         # nd.py handles any dimension through ATen; there is no CPU fallback here
         raise NotImplementedError('interpol_b200 supports 1, 2 or 3 spatial dimensions (got %d)' % dim)
@@ -62,10 +65,19 @@ def _problem(dim, dtype, device, bound, interpolation, extrapolate, batch, chann
         p.order[d] = int(o[d])
         p.vol_shape[d] = int(vol_shape[d])
         p.pts_shape[d] = int(pts_shape[d])
-    p.flags = flags
+    p.flags = flags | (DISPLACEMENT if displacement else 0)
     p.batch = batch
     p.channels = channels
     return p
+
+
+def _dense_grid(grid, dim):
+    """The tiled kernels stage (B, *spatial, D) grids as dense array-of-structs tiles; a strided grid (e.g.
+    component-major, the layout `disp.movedim(1, -1)` leaves behind) runs on the one-thread-per-point kernels,
+    3-4x slower on large 3-D problems than paying one copy of the grid."""
+    if dim == 3 and grid.shape[0] > 0 and grid[0].numel() >= 3 * 32768 and not grid[0].is_contiguous():
+        return grid.contiguous()
+    return grid
 
 
 def _bstride(t, batch):
@@ -108,20 +120,21 @@ def _batch(*tensors):
     return b
 
 
-def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gout=None, gout_comp=False):
+def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gout=None, gout_comp=False,
+            displacement=False):
     _lib.require_cuda(inp, grid, gout)
     dim = grid.shape[-1]
     if grid.dim() != dim + 2 or inp.dim() != dim + 2:
         raise ValueError('expected inp (B, C, *spatial) and grid (B, *spatial, D)')
     dtype = _common_dtype(inp, grid, gout)
     inp = inp.to(dtype)
-    grid = grid.to(dtype)
+    grid = _dense_grid(grid.to(dtype), dim)
     batch = _batch(inp, grid) if gout is None else _batch(inp, grid, gout)
     channels = inp.shape[1]
     ishape = inp.shape[2:]
     oshape = grid.shape[1:-1]
     p = _problem(dim, dtype, grid.device, bound, interpolation, extrapolate, batch, channels,
-                 ishape, oshape)
+                 ishape, oshape, displacement)
     _set_vol(p, inp, batch, dim)
     _set_grid(p, grid, batch, dim)
     L = _lib.lib()
@@ -140,7 +153,7 @@ def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gou
     return out
 
 
-def grid_pull_labels(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int):
+def grid_pull_labels(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int, displacement=False):
     """(B, C, *spatial_in) int32 label map, (B, *spatial_out, D) float32/64 grid -> (B, C, *spatial_out) int32:
     per point, the label whose soft mask interpolates to the largest value (orders 0 / 1).  One pass instead of
     the loop over `input.unique()` of interpol/api.py:194-205."""
@@ -153,7 +166,8 @@ def grid_pull_labels(inp, grid, bound: List[int], interpolation: List[int], extr
     batch = _batch(inp, grid)
     channels = inp.shape[1]
     oshape = grid.shape[1:-1]
-    p = _problem(dim, grid.dtype, grid.device, bound, interpolation, extrapolate, batch, channels, inp.shape[2:], oshape)
+    p = _problem(dim, grid.dtype, grid.device, bound, interpolation, extrapolate, batch, channels, inp.shape[2:], oshape,
+                 displacement)
     _set_vol(p, inp, batch, dim)
     _set_grid(p, grid, batch, dim)
     L = _lib.lib()
@@ -164,42 +178,43 @@ def grid_pull_labels(inp, grid, bound: List[int], interpolation: List[int], extr
     return out
 
 
-def grid_pull(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int):
+def grid_pull(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int, displacement=False):
     """(B, C, *spatial_in), (B, *spatial_out, D) -> (B, C, *spatial_out)
-    Reference: interpol/pushpull.py:35-66."""
-    return _gather('ib200_pull', inp, grid, bound, interpolation, extrapolate, lambda d: [])
+    Reference: interpol/pushpull.py:35-66.  `displacement`: the grid holds displacements (every function below)."""
+    return _gather('ib200_pull', inp, grid, bound, interpolation, extrapolate, lambda d: [], displacement=displacement)
 
 
-def grid_grad(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int):
+def grid_grad(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int, displacement=False):
     """-> (B, C, *spatial_out, D).  Reference: interpol/pushpull.py:146-172."""
-    return _gather('ib200_grad', inp, grid, bound, interpolation, extrapolate, lambda d: [d])
+    return _gather('ib200_grad', inp, grid, bound, interpolation, extrapolate, lambda d: [d], displacement=displacement)
 
 
-def grid_hess(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int):
+def grid_hess(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int, displacement=False):
     """-> (B, C, *spatial_out, D, D).  Reference: interpol/pushpull.py:207-233."""
-    return _gather('ib200_hess', inp, grid, bound, interpolation, extrapolate, lambda d: [d, d])
+    return _gather('ib200_hess', inp, grid, bound, interpolation, extrapolate, lambda d: [d, d], displacement=displacement)
 
 
-def grid_pull_grad_grid(gout, inp, grid, bound, interpolation, extrapolate):
+def grid_pull_grad_grid(gout, inp, grid, bound, interpolation, extrapolate, displacement=False):
     """Fused `(grid_grad(inp, grid) * gout.unsqueeze(-1)).sum(1)` -> (B, *spatial_out, D)
     (the grid branch of interpol/pushpull.py:254-257 without the (B,C,*,D) temporary)."""
-    return _gather('', inp, grid, bound, interpolation, extrapolate, None, gout=gout)
+    return _gather('', inp, grid, bound, interpolation, extrapolate, None, gout=gout, displacement=displacement)
 
 
-def grid_grad_grad_grid(gout, inp, grid, bound, interpolation, extrapolate):
+def grid_grad_grad_grid(gout, inp, grid, bound, interpolation, extrapolate, displacement=False):
     """Fused `(grid_hess(inp, grid) * gout.unsqueeze(-1)).sum(dim=[1, -2])` -> (B, *spatial_out, D), gout
     (B, C, *spatial_out, D): the grid branch of interpol/pushpull.py:318-324 without the (B,C,*,D,D) Hessian."""
-    return _gather('', inp, grid, bound, interpolation, extrapolate, None, gout=gout, gout_comp=True)
+    return _gather('', inp, grid, bound, interpolation, extrapolate, None, gout=gout, gout_comp=True,
+                   displacement=displacement)
 
 
-def _scatter(fn_name, inp, grid, shape, bound, interpolation, extrapolate, comp=False):
+def _scatter(fn_name, inp, grid, shape, bound, interpolation, extrapolate, comp=False, displacement=False):
     _lib.require_cuda(inp, grid)
     dim = grid.shape[-1]
     if grid.dim() != dim + 2:
         raise ValueError('expected grid (B, *spatial, D)')
     gshape = grid.shape[1:-1]
     dtype = _common_dtype(inp, grid)
-    grid = grid.to(dtype)
+    grid = _dense_grid(grid.to(dtype), dim)
     if inp is not None:
         if inp.dim() != dim + 2 + int(comp):
             raise ValueError('expected inp (B, C, *spatial%s)' % (', D' if comp else ''))
@@ -218,7 +233,7 @@ def _scatter(fn_name, inp, grid, shape, bound, interpolation, extrapolate, comp=
     if len(shape) != dim:
         raise ValueError('`shape` should have %d elements' % dim)
     p = _problem(dim, dtype, grid.device, bound, interpolation, extrapolate, batch, channels,
-                 shape, gshape)
+                 shape, gshape, displacement)
     _set_grid(p, grid, batch, dim)
     if inp is not None:
         _set_img(p, inp, batch, dim, comp)
@@ -238,70 +253,72 @@ def _scatter(fn_name, inp, grid, shape, bound, interpolation, extrapolate, comp=
 
 
 def grid_push(inp, grid, shape: Optional[List[int]], bound: List[int], interpolation: List[int],
-              extrapolate: int):
+              extrapolate: int, displacement=False):
     """(B, C, *spatial_in), (B, *spatial_in, D) -> (B, C, *shape)
     Reference: interpol/pushpull.py:70-102."""
-    return _scatter('ib200_push', inp, grid, shape, bound, interpolation, extrapolate)
+    return _scatter('ib200_push', inp, grid, shape, bound, interpolation, extrapolate, displacement=displacement)
 
 
 def grid_count(grid, shape: Optional[List[int]], bound: List[int], interpolation: List[int],
-               extrapolate: int):
+               extrapolate: int, displacement=False):
     """(B, *spatial_in, D) -> (B, 1, *shape).  Reference: interpol/pushpull.py:106-142."""
-    return _scatter('ib200_count', None, grid, shape, bound, interpolation, extrapolate)
+    return _scatter('ib200_count', None, grid, shape, bound, interpolation, extrapolate, displacement=displacement)
 
 
 def grid_pushgrad(inp, grid, shape: List[int], bound: List[int], interpolation: List[int],
-                  extrapolate: int):
+                  extrapolate: int, displacement=False):
     """(B, C, *spatial_in, D) -> (B, C, *shape).  Reference: interpol/pushpull.py:175-204."""
-    return _scatter('ib200_pushgrad', inp, grid, shape, bound, interpolation, extrapolate, comp=True)
+    return _scatter('ib200_pushgrad', inp, grid, shape, bound, interpolation, extrapolate, comp=True,
+                    displacement=displacement)
 
 
 # ---------------------------------------------------------------------------
 # backward compositions (interpol/pushpull.py:237-325)
 # ---------------------------------------------------------------------------
 
-def grid_pull_backward(grad, inp, grid, bound, interpolation, extrapolate):
-    """-> (B, C, *spatial_in), (B, *spatial_out, D).  Reference: pushpull.py:237-258."""
+def grid_pull_backward(grad, inp, grid, bound, interpolation, extrapolate, displacement=False):
+    """-> (B, C, *spatial_in), (B, *spatial_out, D).  Reference: pushpull.py:237-258.
+    (the derivative w.r.t. a displacement equals the derivative w.r.t. the coordinate)"""
     dim = grid.shape[-1]
     grad_inp = grad_grid = None
     if inp.requires_grad:
-        grad_inp = grid_push(grad, grid, inp.shape[-dim:], bound, interpolation, extrapolate)
+        grad_inp = grid_push(grad, grid, inp.shape[-dim:], bound, interpolation, extrapolate, displacement)
     if grid.requires_grad:
-        grad_grid = grid_pull_grad_grid(grad, inp, grid, bound, interpolation, extrapolate)
+        grad_grid = grid_pull_grad_grid(grad, inp, grid, bound, interpolation, extrapolate, displacement)
     return grad_inp, grad_grid
 
 
-def grid_push_backward(grad, inp, grid, bound, interpolation, extrapolate):
+def grid_push_backward(grad, inp, grid, bound, interpolation, extrapolate, displacement=False):
     """-> (B, C, *spatial_in), (B, *spatial_in, D).  Reference: pushpull.py:262-282."""
     grad_inp = grad_grid = None
     if inp.requires_grad:
-        grad_inp = grid_pull(grad, grid, bound, interpolation, extrapolate)
+        grad_inp = grid_pull(grad, grid, bound, interpolation, extrapolate, displacement)
     if grid.requires_grad:
         # sum_c grad(grad_vol, grid)[b,c] * inp[b,c]: same fused kernel, roles swapped
-        grad_grid = grid_pull_grad_grid(inp, grad, grid, bound, interpolation, extrapolate)
+        grad_grid = grid_pull_grad_grid(inp, grad, grid, bound, interpolation, extrapolate, displacement)
     return grad_inp, grad_grid
 
 
-def grid_count_backward(grad, grid, bound, interpolation, extrapolate):
+def grid_count_backward(grad, grid, bound, interpolation, extrapolate, displacement=False):
     """-> (B, *spatial_in, D).  Reference: pushpull.py:286-299."""
     if grid.requires_grad and grad.shape[1] == 1:
         # one channel (what GridCount produces): the gradient kernels' own fast paths
-        return grid_grad(grad, grid, bound, interpolation, extrapolate)[:, 0]
+        return grid_grad(grad, grid, bound, interpolation, extrapolate, displacement)[:, 0]
     if grid.requires_grad:
         ones = torch.ones([1, 1, *([1] * (grid.dim() - 2))], dtype=grad.dtype, device=grad.device)
         ones = ones.expand([grid.shape[0], grad.shape[1], *grid.shape[1:-1]])
-        return grid_pull_grad_grid(ones, grad, grid, bound, interpolation, extrapolate)
+        return grid_pull_grad_grid(ones, grad, grid, bound, interpolation, extrapolate, displacement)
     return None
 
 
-def grid_grad_backward(grad, inp, grid, bound, interpolation, extrapolate):
+def grid_grad_backward(grad, inp, grid, bound, interpolation, extrapolate, displacement=False):
     """grad (B, C, *spatial_out, D) -> (B, C, *spatial_in), (B, *spatial_out, D).
     Reference: pushpull.py:303-325."""
     dim = grid.shape[-1]
     shape = inp.shape[-dim:]
     grad_inp = grad_grid = None
     if inp.requires_grad:
-        grad_inp = grid_pushgrad(grad, grid, shape, bound, interpolation, extrapolate)
+        grad_inp = grid_pushgrad(grad, grid, shape, bound, interpolation, extrapolate, displacement)
     if grid.requires_grad:
-        grad_grid = grid_grad_grad_grid(grad, inp, grid, bound, interpolation, extrapolate)
+        grad_grid = grid_grad_grad_grid(grad, inp, grid, bound, interpolation, extrapolate, displacement)
     return grad_inp, grad_grid

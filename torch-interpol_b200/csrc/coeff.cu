@@ -101,6 +101,106 @@ __device__ __forceinline__ void filter_line(P s, const int st, const int n, cons
 #undef SW
 }
 
+// Same filter for a float32 line that is contiguous in shared memory, 16-byte aligned, n % 4 == 0: the
+// recursions (and the dct2 boundary sums) move four samples per LDS.128 / STS.128.  With rows padded to n + 4
+// words the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups, so the vector accesses are conflict
+// free where scalar accesses at that stride would serialise four ways.  Arithmetic (order of every fma) is that
+// of filter_line.
+__device__ __forceinline__ void filter_line_vec4(float *s, const int n, const CoeffParams &cp, const float gain0) {
+    typedef float R;
+    float4 *s4 = reinterpret_cast<float4 *>(s);
+    const int nv = n >> 2;
+    for (int p = 0; p < cp.npoles; ++p) {
+        const R gn = p == 0 ? gain0 : R(1);
+        const R pole = (R)cp.pole[p];
+        const R pp = (R)cp.pp[p];
+        R init;
+        if (cp.kind == 2) {                      // dct2_initial, coeff.py:153-179
+            const R pn = (R)cp.c1[p];
+            R acc = R(0), a = R(1);
+            const int kmax = n < cp.K2[p] ? n : cp.K2[p];
+            int k = 0;
+            for (; k + 4 <= kmax; k += 4) {
+                const float4 v = s4[k >> 2];
+                acc = fmaf(gn * v.x, a, acc); a *= pp;
+                acc = fmaf(gn * v.y, a, acc); a *= pp;
+                acc = fmaf(gn * v.z, a, acc); a *= pp;
+                acc = fmaf(gn * v.w, a, acc); a *= pp;
+            }
+            for (; k < kmax; ++k) { acc = fmaf(gn * s[k], a, acc); a *= pp; }
+            if (pn != R(0)) {
+                R acc2 = R(0), b = R(1);
+                int q = n - 1;
+                for (; q - 3 >= n - kmax; q -= 4) {
+                    const float4 v = s4[q >> 2];
+                    acc2 = fmaf(gn * v.w, b, acc2); b *= pp;
+                    acc2 = fmaf(gn * v.z, b, acc2); b *= pp;
+                    acc2 = fmaf(gn * v.y, b, acc2); b *= pp;
+                    acc2 = fmaf(gn * v.x, b, acc2); b *= pp;
+                }
+                for (; q >= n - kmax; --q) { acc2 = fmaf(gn * s[q], b, acc2); b *= pp; }
+                acc = fmaf(pn, acc2, acc);
+            }
+            init = fmaf(acc, (R)(cp.pole[p] / (1. - cp.c1[p] * cp.c1[p])), gn * s[0]);
+        } else if (cp.kind == 1) {               // dct1_initial, coeff.py:109-149
+            if (cp.K[p] < n) {
+                R acc = R(0), a = R(1);
+                for (int k = 0; k < cp.K[p]; ++k) { acc = fmaf(gn * s[k], a, acc); a *= pp; }
+                init = acc;
+            } else {
+                const R pn = (R)cp.c1[p];
+                const R pn2 = (R)(cp.c1[p] * cp.c1[p]);
+                R out = gn * s[0] + pn * (gn * s[n - 1]);
+                if (n > 2) {
+                    R acc = R(0), a = pp;
+                    for (int k = 1; k < n - 1; ++k) { acc = fmaf(gn * s[k], a + pn2 / a, acc); a *= pp; }
+                    out += acc;
+                }
+                init = out / (R)(1. - cp.c1[p] * cp.c1[p]);
+            }
+        } else {                                 // dft_initial, coeff.py:82-105
+            R acc = R(0), a = pp;
+            for (int j = 1; j < cp.K[p]; ++j) { acc = fmaf(gn * s[n - j], a, acc); a *= pp; }
+            init = (acc + gn * s[0]) / (R)(1. - cp.c1[p]);
+        }
+        // causal recursion, coeff.py:275-276
+        R prev = init;
+#pragma unroll 2
+        for (int c = 0; c < nv; ++c) {
+            float4 v = s4[c];
+            v.x = c == 0 ? prev : fmaf(pole, prev, gn * v.x);
+            v.y = fmaf(pole, v.x, gn * v.y);
+            v.z = fmaf(pole, v.y, gn * v.z);
+            v.w = fmaf(pole, v.z, gn * v.w);
+            prev = v.w;
+            s4[c] = v;
+        }
+        // final condition (reads the causally filtered line)
+        R fin;
+        if (cp.kind == 1) {                      // dct1_final, coeff.py:210-216
+            fin = (pole * s[n - 2] + s[n - 1]) * (R)(cp.pole[p] / (cp.pole[p] * cp.pole[p] - 1.));
+        } else if (cp.kind == 2) {               // dct2_final, coeff.py:220-227
+            fin = s[n - 1] * (R)(cp.pole[p] / (cp.pole[p] - 1.));
+        } else {                                 // dft_final, coeff.py:183-206
+            R acc = R(0), a = pp * pp;
+            for (int k = 0; k < cp.K[p] - 1; ++k) { acc = fmaf(s[k], a, acc); a *= pp; }
+            fin = fmaf(pole, s[n - 1], acc) / (R)(cp.c1[p] - 1.);
+        }
+        // anti-causal recursion, coeff.py:280-281
+        prev = fin;
+#pragma unroll 2
+        for (int c = nv - 1; c >= 0; --c) {
+            float4 v = s4[c];
+            v.w = c == nv - 1 ? prev : pole * (prev - v.w);
+            v.z = pole * (v.w - v.z);
+            v.y = pole * (v.z - v.y);
+            v.x = pole * (v.y - v.x);
+            prev = v.x;
+            s4[c] = v;
+        }
+    }
+}
+
 // proxy so that filter_line can run directly on 16-bit global storage
 template <typename T>
 struct GlobalRef {
@@ -165,52 +265,64 @@ coeff_strided_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ dat
     }
 }
 
-// inner == 1.  A CTA of 256 threads stages L whole lines (a contiguous block of L*n
-// elements) with an odd row stride, L threads filter one line each, everybody
-// writes back.  Loads are issued 8 deep per thread to cover the HBM latency.
+// inner == 1.  The lines themselves are contiguous.  One warp per CTA owns 32 consecutive lines (a contiguous block
+// of 32 * n elements): float32 blocks are staged with 16-byte cp.async into rows padded to n + 4 words (16-byte
+// aligned rows), every lane filters its own line four samples per LDS.128 / STS.128 (filter_line_vec4: conflict
+// free at that stride), and the block goes back with 16-byte stores.  Several CTAs per SM overlap each other's
+// load / filter / store phases.  Other types (or unaligned blocks) stage element by element with an odd row stride.
 template <typename T>
-__global__ void __launch_bounds__(256)
-coeff_contig_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data, const int row_stride, const int L) {
+__global__ void __launch_bounds__(32)
+coeff_contig_kernel(const __grid_constant__ CoeffParams cp, T *__restrict__ data, const int row_stride, const int vec_ok) {
     typedef typename Traits<T>::Real R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tile = reinterpret_cast<R *>(smem_raw);
-    const int n = (int)cp.n, NT = blockDim.x;
-    const i64 nblk = (cp.outer + L - 1) / L;
+    const int n = (int)cp.n, lane = threadIdx.x;
+    const i64 nblk = (cp.outer + 31) / 32;
     const R gain = (R)cp.gain;
     for (i64 blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const i64 l0 = blk * L;
-        const int nl = (int)((cp.outer - l0) < L ? (cp.outer - l0) : L);
+        const i64 l0 = blk * 32;
+        const int nl = (int)((cp.outer - l0) < 32 ? (cp.outer - l0) : 32);
         T *g = data + l0 * n;
-        const int count = nl * n;
-        // (l, i) of element e = threadIdx.x + k * NT is tracked incrementally: no division
-        const int dl = NT / n, di = NT - dl * n;          // NT = dl * n + di
-        {
-            int l = threadIdx.x / n, i = threadIdx.x - l * n;
-            for (int e0 = threadIdx.x; e0 < count; e0 += NT * 8) {
-                R v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { const int e = e0 + u * NT; v[u] = e < count ? (R)Traits<T>::load_rw(g + e) : R(0); }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (e0 + u * NT < count) tile[l * row_stride + i] = v[u];
-                    l += dl; i += di;
-                    if (i >= n) { i -= n; ++l; }
-                }
+        if (sizeof(T) == 4 && sizeof(R) == 4 && vec_ok) {
+            const int vpl = n >> 2;                       // 16-byte vectors per line
+            const int total = nl * vpl;
+            int l = lane / vpl, v = lane - l * vpl;       // vector e = lane + 32 k  <->  (line l, vector v)
+            const int dl = 32 / vpl, dv = 32 - dl * vpl;
+            for (int e = lane; e < total; e += 32) {
+                cpa16(tile + l * row_stride + 4 * v, g + 4 * (i64)e);
+                l += dl; v += dv;
+                if (v >= vpl) { v -= vpl; ++l; }
             }
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < nl) filter_line<R>(tile + threadIdx.x * row_stride, 1, n, cp, gain);
-        __syncthreads();
-        {
-            int l = threadIdx.x / n, i = threadIdx.x - l * n;
-#pragma unroll 4
-            for (int e = threadIdx.x; e < count; e += NT) {
+            cpa_wait_all();
+            __syncwarp();
+            if (lane < nl) filter_line_vec4(reinterpret_cast<float *>(tile) + lane * row_stride, n, cp, (float)gain);
+            __syncwarp();
+            l = lane / vpl; v = lane - l * vpl;
+            for (int e = lane; e < total; e += 32) {
+                *reinterpret_cast<float4 *>(g + 4 * (i64)e) = *reinterpret_cast<const float4 *>(tile + l * row_stride + 4 * v);
+                l += dl; v += dv;
+                if (v >= vpl) { v -= vpl; ++l; }
+            }
+        } else {
+            const int count = nl * n;
+            int l = lane / n, i = lane - l * n;
+            const int dl = 32 / n, di = 32 - dl * n;
+            for (int e = lane; e < count; e += 32) {
+                tile[l * row_stride + i] = (R)Traits<T>::load_rw(g + e);
+                l += dl; i += di;
+                if (i >= n) { i -= n; ++l; }
+            }
+            __syncwarp();
+            if (lane < nl) filter_line<R>(tile + lane * row_stride, 1, n, cp, gain);
+            __syncwarp();
+            l = lane / n; i = lane - l * n;
+            for (int e = lane; e < count; e += 32) {
                 Traits<T>::store(g + e, tile[l * row_stride + i]);
                 l += dl; i += di;
                 if (i >= n) { i -= n; ++l; }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -276,16 +388,15 @@ static int launch_typed(const CoeffParams &cp, void *data, cudaStream_t stream) 
             return IB200_OK;
         }
     } else {
-        int row_stride = (int)cp.n | 1;   // odd stride: lane l, element i -> distinct banks
-        int L = 64;
-        while (L > 8 && (size_t)L * row_stride * sizeof(R) > 72 * 1024) L >>= 1;
-        const size_t smem = (size_t)L * row_stride * sizeof(R);
+        const int vec_ok = sizeof(T) == 4 && sizeof(R) == 4 && ((uintptr_t)data % 16 == 0) && (cp.n % 4 == 0);
+        const int row_stride = vec_ok ? (int)cp.n + 4 : ((int)cp.n | 1);   // 16-byte aligned rows / odd stride
+        const size_t smem = (size_t)32 * row_stride * sizeof(R);
         if (smem <= kSmemCap) {
-            i64 blocks = (cp.outer + L - 1) / L;
-            const i64 cap = (i64)kNumSMs * 16;
+            i64 blocks = (cp.outer + 31) / 32;
+            const i64 cap = (i64)kNumSMs * 32;
             if (blocks > cap) blocks = cap;
             IB200_CUDA_CHECK(cudaFuncSetAttribute(coeff_contig_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            coeff_contig_kernel<T><<<(unsigned)blocks, 256, smem, stream>>>(cp, d, row_stride, L);
+            coeff_contig_kernel<T><<<(unsigned)blocks, 32, smem, stream>>>(cp, d, row_stride, vec_ok);
             note_launch("coeff_contig");
             IB200_CUDA_CHECK(cudaGetLastError());
             return IB200_OK;

@@ -80,7 +80,7 @@ def test_pipe_matches_generic(order, case):
             a = _with_flags(pp, FORCE_PIPE, lambda: fn(vol, grid, bound, [order], ex))
             assert 'pipe3d' in ib.last_kernel(), ib.last_kernel()
             b = _with_flags(pp, NO_TILES, lambda: fn(vol, grid, bound, [order], ex))
-            assert 'pipe' not in ib.last_kernel() and 'tile' not in ib.last_kernel()
+            assert 'box' not in ib.last_kernel() and 'tile' not in ib.last_kernel()
             scale = b.abs().max().item()
             if scale == 0:
                 assert a.abs().max().item() == 0
@@ -134,12 +134,12 @@ def test_pipe_push_count_vs_oracle(order, bound, extrapolate):
     grid = smooth_grid(shape, gen, amp=4.0, batch=B)
     grid = (grid * torch.tensor([vshape[d] / shape[d] for d in range(3)]) - 1.5).contiguous()    # leaves the field of view
     b, o = [bound, (bound + 1) % 7, (bound + 3) % 7], [order]
-    got = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_push(img.cuda(), grid.cuda(), list(vshape), b, o, extrapolate))
-    assert ib.last_kernel().startswith('push_pipe3d'), ib.last_kernel()
+    got = pp.grid_push(img.cuda(), grid.cuda(), list(vshape), b, o, extrapolate)
+    assert ib.last_kernel().startswith('push_box3d'), ib.last_kernel()
     want = oracle.grid_push(img.double().numpy(), grid.double().numpy(), vshape, b, o, extrapolate)
     assert rel_err(to_np(got), want) <= 1e-5
-    got = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_count(grid.cuda(), list(vshape), b, o, extrapolate))
-    assert ib.last_kernel().startswith('count_pipe3d'), ib.last_kernel()
+    got = pp.grid_count(grid.cuda(), list(vshape), b, o, extrapolate)
+    assert ib.last_kernel().startswith('count_box3d'), ib.last_kernel()
     want = oracle.grid_count(grid.double().numpy(), vshape, b, o, extrapolate)
     assert rel_err(to_np(got), want) <= 1e-5
 
@@ -178,10 +178,10 @@ def test_pipe_push_matches_generic(order, case):
         for count in (False, True):
             fn = (lambda: pp.grid_count(grid, list(shape), bound, [order], ex)) if count else \
                  (lambda: pp.grid_push(img, grid, list(shape), bound, [order], ex))
-            a = _with_flags(pp, FORCE_PIPE, fn)
-            assert 'pipe3d' in ib.last_kernel(), ib.last_kernel()
+            a = fn()
+            assert 'box3d' in ib.last_kernel(), ib.last_kernel()
             b = _with_flags(pp, NO_TILES, fn)
-            assert 'pipe' not in ib.last_kernel() and 'tile' not in ib.last_kernel()
+            assert 'box' not in ib.last_kernel() and 'tile' not in ib.last_kernel()
             scale = b.abs().max().item()
             if scale == 0:
                 assert a.abs().max().item() == 0
@@ -190,7 +190,7 @@ def test_pipe_push_matches_generic(order, case):
 
 
 def test_pipe_push_full_size_adjoint():
-    """256^3 cubic (the bench workload): <pull(x), y> == <x, push(y)> with both pipe kernels"""
+    """256^3 cubic (the bench workload): <pull(x), y> == <x, push(y)> with the persistent pull and the boxed push"""
     import interpol_b200 as ib
     from interpol_b200 import pushpull as pp
     import sys, os
@@ -201,15 +201,15 @@ def test_pipe_push_full_size_adjoint():
     for bound in ([3], [6], [0], [1, 2, 4]):
         px = pp.grid_pull(vol, grid, bound, [3], 1)
         assert ib.last_kernel().startswith('pull_pipe3d')
-        py = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_push(y, grid, [256] * 3, bound, [3], 1))
-        assert ib.last_kernel().startswith('push_pipe3d')
+        py = pp.grid_push(y, grid, [256] * 3, bound, [3], 1)
+        assert ib.last_kernel().startswith('push_box3d')
         lhs = (px.double() * y.double()).sum().item()
         rhs = (vol.double() * py.double()).sum().item()
         scale = (px.double().abs() * y.double().abs()).sum().item()
         assert abs(lhs - rhs) <= 5e-6 * scale, (bound, lhs, rhs, scale)
-    cnt = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_count(grid, [256] * 3, [6], [3], 1))
-    assert ib.last_kernel().startswith('count_pipe3d')
+    cnt = pp.grid_count(grid, [256] * 3, [6], [3], 1)
+    assert ib.last_kernel().startswith('count_box3d')
     assert abs(cnt.double().sum().item() - 256 ** 3) <= 1e-6 * 256 ** 3
-    ref = pp.grid_count(grid, [256] * 3, [6], [3], 1)
-    assert ib.last_kernel().startswith(('count_tile3d', 'count_box3d'))
+    ref = _with_flags(pp, NO_PIPE, lambda: pp.grid_count(grid, [256] * 3, [6], [3], 1))
+    assert ib.last_kernel().startswith('count_tile3d')
     assert rel_err(to_np(cnt), to_np(ref)) <= 4e-6

@@ -43,7 +43,7 @@ DTYPES = {
 def units():
     """(source, object name, extra defines)"""
     out = [('abi.cu', 'abi.o', []), ('coeff.cu', 'coeff.o', [])]
-    for extra in ('pull_tile.cu', 'push_tile.cu', 'pull_pipe.cu', 'push_pipe.cu', 'push_box.cu', 'resample.cu', 'labels.cu'):
+    for extra in ('pull_tile.cu', 'push_tile.cu', 'pull_pipe.cu', 'push_box.cu', 'resample.cu', 'labels.cu'):
         if os.path.exists(os.path.join(CSRC, extra)):
             out.append((extra, extra.replace('.cu', '.o'), []))
     for name, (ctype, acc, orders) in DTYPES.items():

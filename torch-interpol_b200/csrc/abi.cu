@@ -176,9 +176,7 @@ static int run_scatter(int op, const ib200_problem *p, const void *img, const vo
         void *acc = half ? scratch : out;
         const i64 n = kp.batch * kp.channels * kp.vol_total;
         IB200_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n * sizeof(float), s));
-        st = try_push_pipe(op, kp, p->dtype, img, grid, acc, s);
-        if (st < 0) return st;
-        if (st == 0) st = try_push_box(op, kp, p->dtype, img, grid, acc, s);
+        st = try_push_box(op, kp, p->dtype, img, grid, acc, s);
         if (st < 0) return st;
         if (st == 0) st = try_push_tiled(op, kp, p->dtype, img, grid, acc, s);
         if (st < 0) return st;

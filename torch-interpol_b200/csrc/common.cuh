@@ -113,8 +113,6 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
 bool push_tiled_applicable(int op, const KParams &kp, int dtype);
 int try_push_tiled(int op, const KParams &kp, int dtype, const void *img, const void *grid,
                    void *acc, cudaStream_t stream);   // acc: zero-filled float32 accumulation volume
-int try_push_pipe(int op, const KParams &kp, int dtype, const void *img, const void *grid,
-                  void *acc, cudaStream_t stream);   // acc: zero-filled float32 accumulation volume
 int try_push_box(int op, const KParams &kp, int dtype, const void *img, const void *grid,
                  void *acc, cudaStream_t stream);    // acc: zero-filled float32 accumulation volume
 int convert_from_f32(int dtype, const void *src, void *dst, i64 n, cudaStream_t stream);

@@ -1,13 +1,13 @@
-// Building blocks of the persistent, warp-specialised ("pipe") kernels: mbarrier, TMA tile-copy and
-// bulk-reduction wrappers, the geometry of a staged box (planning from a bounding box of support
-// starts, boundary handling modes), the fix-up / fold passes for what the TMA unit cannot express,
+// Building blocks of the persistent, warp-specialised ("pipe") kernels: mbarrier and TMA tile-copy
+// wrappers, the geometry of a staged box (planning from a bounding box of support
+// starts, boundary handling modes), the fix-up pass for what the TMA unit cannot express,
 // and the host-side tensor-map encoder.
 //
-// One CTA per SM (pull) or two (push) loop over tiles of TX x TY x TZ lattice points.  The last warp
+// One CTA per SM loops over tiles of TX x TY x TZ lattice points.  The last warp
 // is the producer: it streams the grid coordinates of upcoming tiles into a ring of shared-memory
 // buffers (one cp.async.bulk.tensor per tile), turns the bounding box the consumers reduced for a
 // tile into a plan (whole tile / z halves / z quarters), and requests one TMA box per x-plane of the
-// input volume (pull) or publishes the geometry of the accumulator box (push).  All other warps are
+// input volume.  (push_box.cu shares the TMA wrappers and the tensor-map encoder.)  All other warps are
 // consumers: they only ever wait on mbarriers and counters, so the tap loop of tile n overlaps with
 // every memory phase of tiles n+1, n+2.
 #pragma once
@@ -44,13 +44,6 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
-// global -> shared, 16-byte aligned on both sides, bytes % 16 == 0; completion is
-// signalled on `bar` as a transaction count
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 // tiled tensor copies (TMA): coordinates innermost first, out-of-bounds elements are zero-filled
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3,
                                             unsigned long long *bar) {
@@ -67,20 +60,8 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *tm, in
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(tm) : "memory");
 }
-// shared -> global element-wise float add (bulk reduction through the TMA engine)
-__device__ __forceinline__ void bulk_red_add_f32(float *dst, const void *src, unsigned bytes) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n"
-                 ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
 // order generic-proxy shared-memory accesses before later async-proxy accesses
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // ---- geometry of one staged box ---------------------------------------------
 // A box is [<= kBoxX planes][kBoxY rows][kBoxZ words], loaded plane by plane with one
@@ -316,55 +297,6 @@ __device__ __forceinline__ void pipe_fixup_plane(const KParams &kp, const PipeGe
                 val[k] = (float)sg * t;
             }
             *reinterpret_cast<float4 *>(dstrow + 4 * v) = make_float4(val[0], val[1], val[2], val[3]);
-        }
-    }
-}
-
-// Adjoint of pipe_fixup_plane for the scatter kernels: x-plane `a` of a box of fixed-point
-// accumulators.  Whatever was accumulated outside the volume (along an axis whose fold neither
-// the TMA clip, nor the x-plane coordinate, nor the z table already covers) is added, with its
-// sign, onto its folded target -- inside the box when the target sits there (integer shared
-// atomic, exact), in global memory otherwise -- and then cleared so that the flush adds nothing.
-__device__ __forceinline__ void push_fold_plane(const KParams &kp, const PipeGeom &g, int *bx, float *dst, int a, float inv) {
-    const int lane = threadIdx.x & 31;
-    const int vpr = (g.ext[2] + 3) >> 2;
-    const int sx = g.lo[0] + a;
-    const int fx = bound_index<int>(kp.bound[0], sx, kp.vol_n[0]);
-    const int sgx = bound_sign<int>(kp.bound[0], sx, kp.vol_n[0]);
-    const bool x_in = a >= g.r0[0] && a < g.r1[0];
-    const int ax = x_in ? a : fx - g.lo[0];
-    const bool x_dst = x_in || (ax >= g.r0[0] && ax < g.r1[0]);
-    const bool z_all = g.r0[2] == 0 && g.r1[2] == vpr;
-    for (int bb = lane >> 1; bb < g.ext[1]; bb += 16) {
-        const bool y_in = bb >= g.r0[1] && bb < g.r1[1];
-        if (x_in && y_in && z_all) continue;
-        const int sy = g.lo[1] + bb;
-        const int fy = bound_index<int>(kp.bound[1], sy, kp.vol_n[1]);
-        const int sgxy = sgx * bound_sign<int>(kp.bound[1], sy, kp.vol_n[1]);
-        const int by = fy - g.lo[1];
-        const bool xy_dst = x_dst && by >= g.r0[1] && by < g.r1[1];
-        int *brow = bx + ax * kBoxPlane + by * kBoxZ;
-        float *grow = dst + fx * (int)kp.vol_s[0] + fy * (int)kp.vol_s[1];
-        int *srcrow = bx + a * kBoxPlane + bb * kBoxZ;
-        for (int v = lane & 1; v < vpr; v += 2) {
-            const bool v_in = v >= g.r0[2] && v < g.r1[2];
-            if (x_in && y_in && v_in) continue;
-            const int4 iv = *reinterpret_cast<const int4 *>(srcrow + 4 * v);
-            if ((iv.x | iv.y | iv.z | iv.w) == 0) continue;
-            const int vals[4] = {iv.x, iv.y, iv.z, iv.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (vals[k] == 0) continue;
-                const int sz = g.lo[2] + 4 * v + k;
-                if (g.zfold && sz > kp.vol_n[2] - 1) continue;                 // padding of a folded box: never written
-                const int fz = g.zfold ? sz : bound_index<int>(kp.bound[2], sz, kp.vol_n[2]);
-                const int sg = g.zfold ? sgxy : sgxy * bound_sign<int>(kp.bound[2], sz, kp.vol_n[2]);
-                if (sg == 0) continue;
-                const int zz = fz - g.lo[2];
-                if (xy_dst && zz >= 4 * g.r0[2] && zz < 4 * g.r1[2]) atomicAdd(brow + zz, sg * vals[k]);
-                else atomicAdd(grow + fz, (float)(sg * vals[k]) * inv);
-            }
-            *reinterpret_cast<int4 *>(srcrow + 4 * v) = make_int4(0, 0, 0, 0);
         }
     }
 }

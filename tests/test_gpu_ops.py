@@ -474,3 +474,56 @@ def test_real_reference_forwards_through_the_seam():
             assert rel_err(to_np(got[k]), want[k].numpy()) <= 1e-5, k
     finally:
         ref.backend.jitfields = False
+
+
+# ------------------------------------------------------------- host tensors --
+
+@pytest.mark.parametrize('pinned', [True, False])
+def test_host_tensors_streamed_equals_plain(pinned, monkeypatch):
+    """CPU tensors: the slab-streamed pull / grad (upload, gather and download overlapped, api._sample_streamed)
+    returns what one upload + one launch returns (to rounding: a slab may take another kernel than the whole
+    lattice), inside and outside a stage_scope, and leaves the device twins the next call of the scope needs."""
+    import interpol_b200 as ib
+    from interpol_b200 import api
+    gen = torch.Generator().manual_seed(77)
+    shape, vshape = (44, 20, 24), (30, 22, 26)
+    vol = torch.randn([2, 2, *vshape], generator=gen)
+    grid = smooth_grid(shape, gen, amp=3.0, batch=2).contiguous()
+    if pinned:
+        vol, grid = vol.pin_memory(), grid.pin_memory()
+    kw = dict(interpolation=3, bound=['dct2', 'dft', 'zero'], extrapolate=True)
+    plain_pull = ib.grid_pull(vol, grid, prefilter=True, **kw)
+    plain_grad = ib.grid_grad(vol, grid, **kw)
+    assert plain_pull.device.type == 'cpu'
+    monkeypatch.setattr(api, 'STREAM_MIN_BYTES', 1)
+    monkeypatch.setattr(api, 'STREAM_SLAB_BYTES', 16 << 10)
+    assert api._streamable(vol, grid, False)
+    got = ib.grid_pull(vol, grid, prefilter=True, **kw)
+    assert got.device.type == 'cpu' and got.shape == plain_pull.shape
+
+    def close(a, b):
+        return rel_err(a.double().numpy(), b.double().numpy()) <= 3e-6
+    assert close(got, plain_pull)
+    assert close(ib.grid_grad(vol, grid, **kw), plain_grad)
+    # no channel / batch axes, ragged last slab
+    v1, g1 = vol[0, 0].contiguous(), grid[0, :37].contiguous()
+    monkeypatch.setattr(api, 'STREAM_MIN_BYTES', 1 << 40)
+    want = ib.grid_pull(v1, g1, **kw)
+    monkeypatch.setattr(api, 'STREAM_MIN_BYTES', 1)
+    got = ib.grid_pull(v1, g1, **kw)
+    assert got.shape == (37, 20, 24) and close(got, want)
+    # inside a scope: the push that follows finds the grid and the pulled image on the device
+    with ib.stage_scope() as scope:
+        pulled = ib.grid_pull(vol, grid, **kw)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        assert scope.lookup(grid, dev) is not None and scope.lookup(pulled, dev) is not None
+        pushed = ib.grid_push(pulled, grid, shape=list(vshape), **kw)
+    monkeypatch.setattr(api, 'STREAM_MIN_BYTES', 1 << 40)
+    with ib.stage_scope():
+        pulled0 = ib.grid_pull(vol, grid, **kw)
+        pushed0 = ib.grid_push(pulled0, grid, shape=list(vshape), **kw)
+    assert close(pulled, pulled0) and close(pushed, pushed0)
+    # tensors that need gradients, displacement fields and device tensors keep the plain path
+    assert not api._streamable(vol.clone().requires_grad_(), grid, False)
+    assert not api._streamable(vol, grid, True)
+    assert not api._streamable(vol.cuda(), grid.cuda(), False)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Phase timers of the pull pipe kernel (CTA 0: producer warp and consumer warp 0), in SM clock ticks.
-    python profiles/pipe_debug.py [--order N] [--channels C] [--bound B]"""
+    python profiles/pipe_debug.py [--order N] [--channels C] [--bound B]
+The timers are compiled in only when the library is built with IB200_TUNE=1 (python torch-interpol_b200/build.py --force)."""
 import ctypes, os, sys
 os.environ['IB200_PIPE_DEBUG'] = '1'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -30,8 +30,18 @@ namespace ib200 {
 // Phase timers (clock64 ticks, accumulated in registers by the producer warp and consumer warp 0 of
 // CTA 0, written once at kernel exit) -- filled only when IB200_PIPE_DEBUG is set in the environment.
 __device__ long long g_pipe_dbg[16];
+// (compiled in with -DIB200_PIPE_TIMERS only -- IB200_TUNE builds, profiles/pipe_debug.py: the clock reads and
+// their predicated adds were ~30 instructions per warp and tile on the consumers' path)
+#if defined(IB200_TUNE) && !defined(IB200_PIPE_TIMERS)
+#define IB200_PIPE_TIMERS
+#endif
+#ifdef IB200_PIPE_TIMERS
 #define TICK(var) const long long var = dbg ? clock64() : 0
 #define TOCK(acc, var) do { if (dbg) acc += clock64() - (var); } while (0)
+#else
+#define TICK(var) do { } while (0)
+#define TOCK(acc, var) do { } while (0)
+#endif
 
 constexpr int kNG = 4;     // ring of grid-coordinate tiles
 constexpr int kNB = 2;     // ring of boxes
@@ -142,7 +152,9 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
         if (my_tiles > 0) request_grid(0);
         if (my_tiles > 1) request_grid(1);
         int n = 0;                                   // box sequence number
+#ifdef IB200_PIPE_TIMERS
         long long a_kfull = 0, a_plan = 0, a_grid = 0, a_bempty = 0, a_issue = 0;
+#endif
         for (int j = 0; j < my_tiles; ++j) {
             int b, x0, y0, z0;
             decode(j, b, x0, y0, z0);
@@ -217,7 +229,9 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                 }
             }
         }
+#ifdef IB200_PIPE_TIMERS
         if (dbg && blockIdx.x == 0 && lane == 0) { dbg[0] = a_kfull; dbg[1] = a_plan; dbg[2] = a_grid; dbg[3] = a_bempty; dbg[4] = a_issue; }
+#endif
     } else {
         // ================================ consumers ===============================
             const bool masked = kp.extrapolate != 1;
@@ -231,7 +245,9 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
             if (lane == 0) mbar_arrive(kfull + (q & 1));
         }
         int n = 0;
+#ifdef IB200_PIPE_TIMERS
         long long a_gfull = 0, a_bfull = 0, a_fix = 0, a_rows = 0, a_rel = 0, a_items = 0;
+#endif
         TICK(t_all);
         for (int q = 0; q < my_tiles; ++q) {
             int b, x0, y0, z0;
@@ -253,8 +269,11 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
             }
             for (int c = 0; c < C; ++c) {
                 const float *src = vol + (i64)b * kp.vol_sb + (i64)c * kp.vol_sc;
-                float *dst = out + ((i64)b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1);
-                const float *gm = BWD ? gout + (i64)b * kp.img_sb + (i64)c * kp.img_sc : nullptr;
+                // lattice offset of this lane's voxel in row 0 of the tile (32-bit: pts_total * 3 < 2^31)
+                const int o0 = (x0 * kp.pts_n[1] + y0) * kp.pts_n[2] + z0 + lane;
+                float *dst = out + ((i64)b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1) + (GRAD ? 3 * o0 : o0);
+                const float *gm = BWD ? gout + (i64)b * kp.img_sb + (i64)c * kp.img_sc + o0 : nullptr;
+                const int ostride_y = kp.pts_n[2], ostride_x = kp.pts_n[1] * kp.pts_n[2];
                 bool last;
                 do {
                     const int s = n % kNB;
@@ -291,13 +310,13 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                         int rn = 0;
                         if (lane == 0) rn = atomicAdd(rowctr + s, 1);      // claimed early: its latency hides behind the taps
                         const int p = r / TY, ly = r - p * TY;
-                        if (look) {
+                        if (look && p < nxv2 && ly < nyv2 && lane < nzv2) {
                             const float c2[3] = {gt2[r * (TZ * 3)], gt2[r * (TZ * 3) + 1], gt2[r * (TZ * 3) + 2]};
-                            const bool use = p < nxv2 && ly < nyv2 && lane < nzv2 && (!masked || inbounds<float, 3>(kp, c2));
+                            bool use = true;
+                            if (masked) use = inbounds<float, 3>(kp, c2);
+                            if (use) {
 #pragma unroll
-                            for (int d = 0; d < 3; ++d) {
-                                mn[d] = fminf(mn[d], use ? c2[d] : 3e38f);
-                                mx[d] = fmaxf(mx[d], use ? c2[d] : -3e38f);
+                                for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], c2[d]); mx[d] = fmaxf(mx[d], c2[d]); }
                             }
                         }
                         if (p < nxv && ly < nyv && lane_ok) {
@@ -403,7 +422,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                                     else { res[0] = ax_; res[1] = ay_; res[2] = az_; }
                                 }
                             }
-                            const int o = ((x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lane);
+                            const int o = p * ostride_x + ly * ostride_y;
                             if (BWD) { const float m = gm[o]; res[0] *= m; res[1] *= m; res[2] *= m; }
                             if (!GRAD) dst[o] = res[0];
                             else { dst[o * 3] = res[0]; dst[o * 3 + 1] = res[1]; dst[o * 3 + 2] = res[2]; }
@@ -428,14 +447,18 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     }
                     ++n;
                     TOCK(a_rel, t_e);
+#ifdef IB200_PIPE_TIMERS
                     a_items += 1;
+#endif
                 } while (!last);
             }
         }
+#ifdef IB200_PIPE_TIMERS
         if (dbg && blockIdx.x == 0 && warp == 0 && lane == 0) {
             dbg[5] = a_gfull; dbg[6] = a_bfull; dbg[7] = a_fix; dbg[8] = a_rows; dbg[9] = a_rel; dbg[10] = a_items;
             dbg[11] = clock64() - t_all;
         }
+#endif
     }
 }
 

@@ -141,38 +141,41 @@ def test_option_parsing_matches_reference_tables():
 
 
 def test_shape_algebra():
-    """api._preproc/_postproc (api.py:93-146), utils.expanded_shape, pad_list_int"""
-    from interpol_b200.api import _preproc, _postproc
+    """api._Layout (the shape conventions of api.py:93-146), utils.expanded_shape, pad_list_int"""
+    from interpol_b200.api import _Layout
     from interpol_b200.utils import expanded_shape, make_list
     from interpol_b200.pushpull import pad_list_int
     assert pad_list_int([1], 3) == [1, 1, 1] and pad_list_int([1, 2, 3, 4], 2) == [1, 2]
     assert expanded_shape((2, 1, 3), (4, 3)) == (2, 4, 3)
+    assert expanded_shape((2, 3), (1, 1, 5), side='right') == (2, 3, 5)
+    assert expanded_shape((0, 3), (1, 3)) == (0, 3) and expanded_shape() == ()
     with pytest.raises(ValueError):
         expanded_shape((2, 3), (4, 3))
+    with pytest.raises(ValueError):
+        expanded_shape((0, 3), (4, 3))
     assert make_list(1, 3) == [1, 1, 1] and make_list([1, 2], 3) == [1, 2, 2]
     # no batch, no channel
-    grid, inp, info = _preproc(torch.zeros(5, 6, 2), torch.zeros(7, 8))
-    assert grid.shape == (1, 5, 6, 2) and inp.shape == (1, 1, 7, 8)
-    assert _postproc(torch.zeros(1, 1, 5, 6), info, 'pull').shape == (5, 6)
+    lay = _Layout(torch.zeros(5, 6, 2), torch.zeros(7, 8))
+    assert lay.grid.shape == (1, 5, 6, 2) and lay.volume.shape == (1, 1, 7, 8) and lay.dim == 2
+    assert lay.restore(torch.zeros(1, 1, 5, 6)).shape == (5, 6)
     # channel, broadcast batch (zero-stride expand, no copy)
     base = torch.zeros(3, 7, 8)
-    grid, inp, info = _preproc(torch.zeros(4, 5, 6, 2), base)
-    assert grid.shape == (4, 5, 6, 2) and inp.shape == (4, 3, 7, 8) and inp.stride(0) == 0
-    assert inp.data_ptr() == base.data_ptr()
-    assert _postproc(torch.zeros(4, 3, 5, 6), info, 'pull').shape == (4, 3, 5, 6)
-    assert _postproc(torch.zeros(4, 3, 5, 6, 2), info, 'grad').shape == (4, 3, 5, 6, 2)
+    lay = _Layout(torch.zeros(4, 5, 6, 2), base)
+    assert lay.grid.shape == (4, 5, 6, 2) and lay.volume.shape == (4, 3, 7, 8) and lay.volume.stride(0) == 0
+    assert lay.volume.data_ptr() == base.data_ptr()
+    assert lay.restore(torch.zeros(4, 3, 5, 6)).shape == (4, 3, 5, 6)
+    assert lay.restore(torch.zeros(4, 3, 5, 6, 2)).shape == (4, 3, 5, 6, 2)         # grad: trailing feature axis
     # multiple batch axes
-    grid, inp, info = _preproc(torch.zeros(2, 1, 5, 6, 2), torch.zeros(3, 4, 7, 8))
-    assert grid.shape == (6, 5, 6, 2) and inp.shape == (6, 4, 7, 8)
-    assert _postproc(torch.zeros(6, 4, 5, 6), info, 'pull').shape == (2, 3, 4, 5, 6)
+    lay = _Layout(torch.zeros(2, 1, 5, 6, 2), torch.zeros(3, 4, 7, 8))
+    assert lay.grid.shape == (6, 5, 6, 2) and lay.volume.shape == (6, 4, 7, 8)
+    assert lay.restore(torch.zeros(6, 4, 5, 6)).shape == (2, 3, 4, 5, 6)
     # push: spatial shapes broadcast together (api.py:118-119)
-    grid, inp, info = _preproc(torch.zeros(5, 6, 2), torch.zeros(3, 1, 6), mode='push')
-    assert inp.shape == (1, 3, 5, 6)
+    lay = _Layout(torch.zeros(5, 6, 2), torch.zeros(3, 1, 6), splat=True)
+    assert lay.volume.shape == (1, 3, 5, 6)
     # count
-    grid, info = _preproc(torch.zeros(2, 5, 6, 2))
-    assert grid.shape == (2, 5, 6, 2) and _postproc(torch.zeros(2, 1, 7, 7), info, 'count').shape == (2, 1, 7, 7)
-    grid, info = _preproc(torch.zeros(5, 6, 2))
-    assert _postproc(torch.zeros(1, 1, 7, 7), info, 'count').shape == (7, 7)
+    lay = _Layout(torch.zeros(2, 5, 6, 2))
+    assert lay.grid.shape == (2, 5, 6, 2) and lay.restore(torch.zeros(2, 1, 7, 7)).shape == (2, 1, 7, 7)
+    assert _Layout(torch.zeros(5, 6, 2)).restore(torch.zeros(1, 1, 7, 7)).shape == (7, 7)
 
 
 def test_grid_helpers_cpu():

@@ -224,14 +224,16 @@ def _sample_streamed(fn, mode, input, grid, interpolation, bound, extrapolate, p
     allow it (the caller then takes the plain path)."""
     dev = torch.device('cuda', torch.cuda.current_device())
     dim = grid.shape[-1]
-    grid_c, _, shape_info = _preproc(grid, input)
+    host = _Layout(grid, input)
+    grid_c = host.grid
     if grid_c.numel() != grid.numel() or not grid_c.is_contiguous():
         return None                       # broadcast batch: the plain path uploads the grid once
     (input_d,), _ = _stage(input)         # whole volume, through the scope's twin cache
     main = torch.cuda.current_stream(dev)
     up, down = _side_streams(dev)
     grid_full = torch.empty(grid.shape, dtype=grid.dtype, device=dev)
-    grid_d, input_d, _ = _preproc(grid_full, input_d)
+    dev_layout = _Layout(grid_full, input_d)
+    grid_d, input_d = dev_layout.grid, dev_layout.volume
     if prefilter:
         input_d = spline_coeff_nd(input_d, interpolation=interpolation, bound=bound, dim=dim)
     B, C = input_d.shape[:2]
@@ -259,62 +261,47 @@ def _sample_streamed(fn, mode, input, grid, interpolation, bound, extrapolate, p
                 for c in range(C):
                     out_h[b, c, x0:x1].copy_(out_d[b, c, x0:x1], non_blocking=True)
     down.synchronize()
-    host = _postproc(out_h, shape_info, mode)
+    result = host.restore(out_h)
     scope = _scope()
     if scope is not None:
         scope.remember(grid, grid_full)
-        scope.remember(host, _postproc(out_d, shape_info, mode))
-    return host
+        scope.remember(result, host.restore(out_d))
+    return result
 
 
 # --------------------------------------------------------------------------
-# shape canonicalisation (reference: api.py:93-146)
+# shape canonicalisation
 # --------------------------------------------------------------------------
 
-def _preproc(grid, input=None, mode=None):
-    """Broadcast batch dimensions and reshape to (B, C, *spatial) / (B, *spatial, D).
-    Batch broadcasting uses `expand` (zero strides): the kernels honour strides so
-    no copy is made unless `reshape` has to merge non-mergeable axes."""
-    dim = grid.shape[-1]
-    if input is None:
-        spatial = grid.shape[-dim-1:-1]
-        batch = grid.shape[:-dim-1]
-        grid = grid.reshape([-1, *spatial, dim])
-        info = dict(batch=batch, channel=[1] if batch else [], dim=dim)
-        return grid, info
+class _Layout:
+    """Canonical views of the tensors of one call and the way back.
 
-    grid_spatial = grid.shape[-dim-1:-1]
-    grid_batch = grid.shape[:-dim-1]
-    input_spatial = input.shape[-dim:]
-    channel = 0 if input.dim() == dim else input.shape[-dim-1]
-    input_batch = input.shape[:-dim-1]
+    The kernels want volumes as (B, C, *spatial) and grids as (B, *spatial, D); the public functions accept
+    any leading batch axes (broadcast between volume and grid, as in interpol/api.py:93-146), an optional
+    channel axis, or no leading axes at all.  Broadcasting is done with `expand` (zero strides, which the
+    kernels honour): nothing is copied unless `reshape` has to merge axes that cannot be merged.
+    """
 
-    if mode == 'push':
-        grid_spatial = input_spatial = expanded_shape(grid_spatial, input_spatial)
+    def __init__(self, grid, volume=None, splat=False):
+        self.dim = dim = grid.shape[-1]
+        lattice, lead_g = tuple(grid.shape[-dim - 1:-1]), tuple(grid.shape[:-dim - 1])
+        if volume is None:                           # count: the output has one channel iff there is a batch
+            self.lead, self.channels = lead_g, ([1] if lead_g else [])
+            self.grid, self.volume = grid.reshape([-1, *lattice, dim]), None
+            return
+        vshape = tuple(volume.shape[-dim:])
+        nchan = volume.shape[-dim - 1] if volume.dim() > dim else 0      # 0: no channel axis
+        if splat:                                    # push: the image lives on the grid's lattice
+            lattice = vshape = expanded_shape(lattice, vshape)
+        self.lead = lead = expanded_shape(lead_g, tuple(volume.shape[:-dim - 1]))
+        self.channels = [nchan] if nchan else ([1] if lead else [])
+        self.grid = grid.expand([*lead, *lattice, dim]).reshape([-1, *lattice, dim])
+        self.volume = volume.expand([*lead, nchan or 1, *vshape]).reshape([-1, nchan or 1, *vshape])
 
-    batch = expanded_shape(grid_batch, input_batch)
-    grid = grid.expand([*batch, *grid_spatial, dim])
-    grid = grid.reshape([-1, *grid_spatial, dim])
-    input = input.expand([*batch, channel or 1, *input_spatial])
-    input = input.reshape([-1, channel or 1, *input_spatial])
-
-    out_channel = [channel] if channel else ([1] if batch else [])
-    info = dict(batch=batch, channel=out_channel, dim=dim)
-    return grid, input, info
-
-
-def _postproc(out, shape_info, mode):
-    """reference: api.py:133-146"""
-    dim = shape_info['dim']
-    if mode != 'grad':
-        spatial = out.shape[-dim:]
-        feat = []
-    else:
-        spatial = out.shape[-dim-1:-1]
-        feat = [out.shape[-1]]
-    batch = shape_info['batch']
-    channel = shape_info['channel']
-    return out.reshape([*batch, *channel, *spatial, *feat])
+    def restore(self, out, features=0):
+        """(B, C, *spatial[, features]) back to the caller's leading axes."""
+        tail = out.shape[2:]
+        return out.reshape([*self.lead, *self.channels, *tail])
 
 
 LABELS_FUSED = True      # False: always loop over the labels like the reference (A/B testing)
@@ -334,6 +321,23 @@ def _labels_fused_ok(input, grid, interpolation):
         lo, hi = input.amin().item(), input.amax().item()
         return -2 ** 31 <= lo and hi < 2 ** 31
     return False
+
+
+def _pull_labels_by_mask(labels, grid, interpolation, bound, extrapolate, prefilter, displacement):
+    """Label maps beyond what the fused kernel covers (orders >= 2, prefiltered masks): every label present is
+    resampled as a soft mask and each point keeps the label whose mask is largest -- ties and all-zero points go
+    to the label met first in ascending order, and a point no mask reaches stays 0 (interpol/api.py:194-205)."""
+    lattice = grid.shape[1:-1]
+    best = grid.new_zeros([*labels.shape[:2], *lattice])
+    winner = labels.new_zeros(best.shape)
+    for value in labels.unique():
+        mask = (labels == value).to(grid.dtype)
+        if prefilter:
+            mask = spline_coeff_nd(mask, interpolation=interpolation, bound=bound, dim=grid.shape[-1], inplace=True)
+        mask = GridPull.apply(mask, grid, interpolation, bound, extrapolate, displacement)
+        winner[mask > best] = value
+        best = torch.maximum(best, mask)
+    return winner
 
 
 # --------------------------------------------------------------------------
@@ -362,34 +366,23 @@ def grid_pull(input, grid, interpolation='linear', bound='zero',
         if out is not None:
             return out
     (input, grid), back = _stage(input, grid)
-    grid, input, shape_info = _preproc(grid, input)
-    batch, channel = input.shape[:2]
-    dim = grid.shape[-1]
+    layout = _Layout(grid, input)
+    grid, input = layout.grid, layout.volume
+    dim = layout.dim
 
-    if not input.dtype.is_floating_point and _labels_fused_ok(input, grid, interpolation):
+    if input.dtype.is_floating_point:
+        if prefilter:
+            input = spline_coeff_nd(input, interpolation=interpolation, bound=bound, dim=dim)
+        out = GridPull.apply(input, grid, interpolation, bound, extrapolate, displacement)
+    elif _labels_fused_ok(input, grid, interpolation):
         # one pass: every point looks for the arg-max among the labels of its own (order+1)^dim nodes
         from .autograd import _options
         from . import pushpull as _pp
         bnd, order, extr = _options(interpolation, bound, extrapolate)
         out = _pp.grid_pull_labels(input.to(torch.int32), grid, bnd, order, extr, displacement).to(input.dtype)
-    elif not input.dtype.is_floating_point:
-        out = input.new_zeros([batch, channel, *grid.shape[1:-1]])
-        pmax = grid.new_zeros([batch, channel, *grid.shape[1:-1]])
-        for label in input.unique():
-            soft = (input == label).to(grid.dtype)
-            if prefilter:
-                soft = spline_coeff_nd(soft, interpolation=interpolation,
-                                       bound=bound, dim=dim, inplace=True)
-            soft = GridPull.apply(soft, grid, interpolation, bound, extrapolate, displacement)
-            out[soft > pmax] = label
-            pmax = torch.max(pmax, soft)
     else:
-        if prefilter:
-            input = spline_coeff_nd(input, interpolation=interpolation,
-                                    bound=bound, dim=dim)
-        out = GridPull.apply(input, grid, interpolation, bound, extrapolate, displacement)
-
-    return back(_postproc(out, shape_info, mode='pull'))
+        out = _pull_labels_by_mask(input, grid, interpolation, bound, extrapolate, prefilter, displacement)
+    return back(layout.restore(out))
 
 
 def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
@@ -401,17 +394,13 @@ def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
     returns (..., [channel], *shape)        (reference: api.py:215-262)
     """
     (input, grid), back = _stage(input, grid)
-    grid, input, shape_info = _preproc(grid, input, mode='push')
-    dim = grid.shape[-1]
-
+    layout = _Layout(grid, input, splat=True)
     if shape is None:
-        shape = tuple(input.shape[2:])
-
-    out = GridPush.apply(input, grid, shape, interpolation, bound, extrapolate, displacement)
+        shape = tuple(layout.volume.shape[2:])
+    out = GridPush.apply(layout.volume, layout.grid, shape, interpolation, bound, extrapolate, displacement)
     if prefilter:
-        out = spline_coeff_nd(out, interpolation=interpolation, bound=bound,
-                              dim=dim, inplace=True)
-    return back(_postproc(out, shape_info, mode='push'))
+        out = spline_coeff_nd(out, interpolation=interpolation, bound=bound, dim=layout.dim, inplace=True)
+    return back(layout.restore(out))
 
 
 def grid_count(grid, shape=None, interpolation='linear', bound='zero',
@@ -421,9 +410,9 @@ def grid_count(grid, shape=None, interpolation='linear', bound='zero',
     grid : (..., *inshape, dim);  returns (..., [1], *shape)   (reference: api.py:265-299)
     """
     (grid,), back = _stage(grid)
-    grid, shape_info = _preproc(grid)
-    out = GridCount.apply(grid, shape, interpolation, bound, extrapolate, displacement)
-    return back(_postproc(out, shape_info, mode='count'))
+    layout = _Layout(grid)
+    out = GridCount.apply(layout.grid, shape, interpolation, bound, extrapolate, displacement)
+    return back(layout.restore(out))
 
 
 def grid_grad(input, grid, interpolation='linear', bound='zero',
@@ -437,12 +426,12 @@ def grid_grad(input, grid, interpolation='linear', bound='zero',
         if out is not None:
             return out
     (input, grid), back = _stage(input, grid)
-    grid, input, shape_info = _preproc(grid, input)
-    dim = grid.shape[-1]
+    layout = _Layout(grid, input)
+    input = layout.volume
     if prefilter:
-        input = spline_coeff_nd(input, interpolation, bound, dim)
-    out = GridGrad.apply(input, grid, interpolation, bound, extrapolate, displacement)
-    return back(_postproc(out, shape_info, mode='grad'))
+        input = spline_coeff_nd(input, interpolation, bound, layout.dim)
+    out = GridGrad.apply(input, layout.grid, interpolation, bound, extrapolate, displacement)
+    return back(layout.restore(out))
 
 
 def spline_coeff(input, interpolation='linear', bound='dct2', dim=-1,

@@ -97,129 +97,72 @@ def _options(interpolation, bound, extrapolate):
     return bound, interpolation, int(extrapolate)
 
 
-class GridPull(torch.autograd.Function):
-    """reference: interpol/autograd.py:157-184"""
+# The six Functions differ only in which kernels they call and in how many of their leading arguments are
+# tensors, so they are stamped out of two templates.  `.apply` keeps the reference's positional signatures
+# (interpol/autograd.py:157-333); the sampling Functions accept one optional trailing argument, `displacement`
+# (an extension: the grid holds displacements), and return one gradient slot per argument they were given.
 
-    @staticmethod
-    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, input, grid, interpolation, bound, extrapolate, displacement=False):
-        # (`displacement`: optional sixth argument, an extension -- the grid holds displacements)
-        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
-        output = grid_pull(input, grid, *opt)
-        ctx.opt = opt
-        ctx.save_for_backward(input, grid)
-        return output
+def _sampling_function(name, kernel, adjoint, n_tensors, takes_shape, signature, lines):
+    def forward(ctx, *args):
+        tensors, rest = args[:n_tensors], list(args[n_tensors:])
+        shape = [rest.pop(0)] if takes_shape else []
+        interpolation, bound, extrapolate = rest[:3]
+        displacement = bool(rest[3]) if len(rest) > 3 else False
+        ctx.opt = _options(interpolation, bound, extrapolate) + (displacement,)
+        ctx.n_args = len(args)
+        ctx.save_for_backward(*tensors)
+        return kernel(*tensors, *shape, *ctx.opt)
 
-    @staticmethod
-    @custom_bwd(device_type='cuda')
     def backward(ctx, grad):
-        grad_input, grad_grid = grid_pull_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_input, grad_grid, None, None, None, None
+        grads = (None,) * n_tensors
+        if any(ctx.needs_input_grad[:n_tensors]):
+            grads = adjoint(grad, *ctx.saved_tensors, *ctx.opt)
+            if n_tensors == 1:
+                grads = (grads,)
+        return tuple(grads) + (None,) * (ctx.n_args - n_tensors)
+
+    body = {
+        '__doc__': '`%s.apply(%s[, displacement])` -- reference: interpol/autograd.py:%s' % (name, signature, lines),
+        'forward': staticmethod(custom_fwd(device_type='cuda', cast_inputs=torch.float32)(forward)),
+        'backward': staticmethod(custom_bwd(device_type='cuda')(backward)),
+    }
+    return type(name, (torch.autograd.Function,), body)
 
 
-class GridPush(torch.autograd.Function):
-    """reference: interpol/autograd.py:187-214"""
-
-    @staticmethod
-    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, input, grid, shape, interpolation, bound, extrapolate, displacement=False):
-        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
-        output = grid_push(input, grid, shape, *opt)
-        ctx.opt = opt
-        ctx.save_for_backward(input, grid)
-        return output
-
-    @staticmethod
-    @custom_bwd(device_type='cuda')
-    def backward(ctx, grad):
-        grad_input, grad_grid = grid_push_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_input, grad_grid, None, None, None, None, None
+GridPull = _sampling_function('GridPull', grid_pull, grid_pull_backward, 2, False,
+                              'input, grid, interpolation, bound, extrapolate', '157-184')
+GridPush = _sampling_function('GridPush', grid_push, grid_push_backward, 2, True,
+                              'input, grid, shape, interpolation, bound, extrapolate', '187-214')
+GridCount = _sampling_function('GridCount', grid_count, grid_count_backward, 1, True,
+                               'grid, shape, interpolation, bound, extrapolate', '217-245')
+GridGrad = _sampling_function('GridGrad', grid_grad, grid_grad_backward, 2, False,
+                              'input, grid, interpolation, bound, extrapolate', '248-277')
 
 
-class GridCount(torch.autograd.Function):
-    """reference: interpol/autograd.py:217-245"""
-
-    @staticmethod
-    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, grid, shape, interpolation, bound, extrapolate, displacement=False):
-        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
-        output = grid_count(grid, shape, *opt)
-        ctx.opt = opt
-        ctx.save_for_backward(grid)
-        return output
-
-    @staticmethod
-    @custom_bwd(device_type='cuda')
-    def backward(ctx, grad):
-        grad_grid = None
-        if ctx.needs_input_grad[0]:
-            grad_grid = grid_count_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_grid, None, None, None, None, None
-
-
-class GridGrad(torch.autograd.Function):
-    """reference: interpol/autograd.py:248-277"""
-
-    @staticmethod
-    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, input, grid, interpolation, bound, extrapolate, displacement=False):
-        opt = _options(interpolation, bound, extrapolate) + (bool(displacement),)
-        output = grid_grad(input, grid, *opt)
-        ctx.opt = opt
-        ctx.save_for_backward(input, grid)
-        return output
-
-    @staticmethod
-    @custom_bwd(device_type='cuda')
-    def backward(ctx, grad):
-        grad_input = grad_grid = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            grad_input, grad_grid = grid_grad_backward(grad, *ctx.saved_tensors, *ctx.opt)
-        return grad_input, grad_grid, None, None, None, None
-
-
-class SplineCoeff(torch.autograd.Function):
-    """reference: interpol/autograd.py:280-305 (note: bound before interpolation)"""
-
-    @staticmethod
-    @custom_fwd(device_type='cuda')
+def _prefilter_function(name, kernel, per_axis, lines):
+    """`apply(input, bound, interpolation, dim, inplace)` -- note: bound BEFORE interpolation, like the reference.
+    The filter is symmetric, so the backward pass is the same filter applied to the gradient (autograd.py:301-305)."""
     def forward(ctx, input, bound, interpolation, dim, inplace):
-        bound = bound_to_nitorch(make_list(bound)[0], as_type='int')
-        interpolation = inter_to_nitorch(make_list(interpolation)[0], as_type='int')
-        opt = (bound, interpolation, dim, inplace)
+        bound, interpolation = make_list(bound), make_list(interpolation)
+        if not per_axis:
+            bound, interpolation = bound[0], interpolation[0]
+        opt = (bound_to_nitorch(bound, as_type='int'), inter_to_nitorch(interpolation, as_type='int'), dim)
         if inplace:
             ctx.mark_dirty(input)
-        output = spline_coeff(input, *opt)
         if input.requires_grad:
             ctx.opt = opt
-        return output
+        return kernel(input, *opt, inplace)
 
-    @staticmethod
-    @custom_bwd(device_type='cuda')
     def backward(ctx, grad):
-        # symmetric filter -> backward == forward (autograd.py:301-305)
-        grad = spline_coeff(grad, *ctx.opt[:-1], inplace=False)
-        return grad, None, None, None, None
+        return kernel(grad, *ctx.opt, inplace=False), None, None, None, None
+
+    body = {
+        '__doc__': '`%s.apply(input, bound, interpolation, dim, inplace)` -- reference: interpol/autograd.py:%s' % (name, lines),
+        'forward': staticmethod(custom_fwd(device_type='cuda')(forward)),
+        'backward': staticmethod(custom_bwd(device_type='cuda')(backward)),
+    }
+    return type(name, (torch.autograd.Function,), body)
 
 
-class SplineCoeffND(torch.autograd.Function):
-    """reference: interpol/autograd.py:308-333"""
-
-    @staticmethod
-    @custom_fwd(device_type='cuda')
-    def forward(ctx, input, bound, interpolation, dim, inplace):
-        bound = bound_to_nitorch(make_list(bound), as_type='int')
-        interpolation = inter_to_nitorch(make_list(interpolation), as_type='int')
-        opt = (bound, interpolation, dim, inplace)
-        if inplace:
-            ctx.mark_dirty(input)
-        output = spline_coeff_nd(input, *opt)
-        if input.requires_grad:
-            ctx.opt = opt
-        return output
-
-    @staticmethod
-    @custom_bwd(device_type='cuda')
-    def backward(ctx, grad):
-        grad = spline_coeff_nd(grad, *ctx.opt[:-1], inplace=False)
-        return grad, None, None, None, None
+SplineCoeff = _prefilter_function('SplineCoeff', spline_coeff, False, '280-305')
+SplineCoeffND = _prefilter_function('SplineCoeffND', spline_coeff_nd, True, '308-333')

@@ -6,7 +6,8 @@ dense grid + `grid_push`."""
 import torch
 
 from .api import grid_push, _stage
-from .utils import make_list, meshgrid_ij
+from .geometry import SamplingPlan
+from .utils import meshgrid_ij
 
 SEPARABLE = True     # False: always build the dense grid and call grid_push (A/B testing)
 
@@ -20,58 +21,16 @@ def restrict(image, factor=None, shape=None, anchor='c',
     image : (batch, channel, *inshape);  returns (batch, channel, *shape)
     reduce_sum : if False the result is divided by the product of the scales
     """
-    factor = make_list(factor) if factor else []
-    shape = make_list(shape) if shape else []
-    anchor = make_list(anchor)
-    nb_dim = max(len(factor), len(shape), len(anchor)) or (image.dim() - 2)
-    anchor = [a[0].lower() for a in make_list(anchor, nb_dim)]
-    bck = dict(dtype=image.dtype, device=image.device)
-
-    inshape = image.shape[-nb_dim:]
-    if factor:
-        factor = make_list(factor, nb_dim)
-    elif not shape:
-        raise ValueError('One of `factor` or `shape` must be provided')
-    if shape:
-        shape = make_list(shape, nb_dim)
+    plan = SamplingPlan(image, factor, shape, anchor, upsample=False)
+    opts = dict(bound='nearest', extrapolate=True, interpolation=interpolation, prefilter=False)
+    opts.update(kwargs)
+    if _separable_ok(image, plan.ndim, opts):
+        out = _restrict_separable(image, plan.coords, plan.outshape, plan.ndim, **opts)
     else:
-        shape = [int(i/f) for i, f in zip(inshape, factor)]
-    if not factor:
-        factor = [i/o for o, i in zip(shape, inshape)]
-
-    lin = []
-    fullscale = 1
-    for anch, f, inshp, outshp in zip(anchor, factor, inshape, shape):
-        if anch == 'c':
-            lin.append(torch.linspace(0, outshp - 1, inshp, **bck))
-            fullscale *= (inshp - 1) / (outshp - 1)
-        elif anch == 'e':
-            scale = outshp / inshp
-            shift = 0.5 * (scale - 1)
-            fullscale *= scale
-            lin.append(torch.arange(0., inshp, **bck) * scale + shift)
-        elif anch == 'f':
-            fullscale *= 1/f
-            lin.append(torch.arange(0., inshp, **bck) / f)
-        elif anch == 'l':
-            shift = (outshp - 1) - (inshp - 1) / f
-            fullscale *= 1/f
-            lin.append(torch.arange(0., inshp, **bck) / f + shift)
-        else:
-            raise ValueError('Unknown anchor {}'.format(anch))
-
-    kwargs.setdefault('bound', 'nearest')
-    kwargs.setdefault('extrapolate', True)
-    kwargs.setdefault('interpolation', interpolation)
-    kwargs.setdefault('prefilter', False)
-    if _separable_ok(image, nb_dim, kwargs):
-        resized = _restrict_separable(image, lin, shape, nb_dim, **kwargs)
-    else:
-        grid = torch.stack(meshgrid_ij(*lin), dim=-1)
-        resized = grid_push(image, grid, shape, **kwargs)
-    if not reduce_sum:
-        resized = resized / fullscale if resized.requires_grad else resized.div_(fullscale)
-    return resized
+        out = grid_push(image, torch.stack(meshgrid_ij(*plan.coords), dim=-1), plan.outshape, **opts)
+    if reduce_sum:
+        return out
+    return out / plan.scale if out.requires_grad else out.div_(plan.scale)
 
 
 def _separable_ok(image, nb_dim, kwargs):

@@ -15,21 +15,21 @@ def make_list(x, n=None, **kwargs):
 
 
 def expanded_shape(*shapes, side='left'):
-    """Broadcast shapes; raises ValueError when incompatible.
-    Reference: interpol/utils.py:38-78."""
-    nb_dim = max([len(s) for s in shapes], default=0)
-    shape = [1] * nb_dim
-    for shape1 in shapes:
-        pad = [1] * (nb_dim - len(shape1))
-        shape1 = [*pad, *shape1] if side == 'left' else [*shape1, *pad]
-        new = []
-        for s0, s1 in zip(shape, shape1):
-            if s0 != 1 and s1 != 1 and s0 != s1:
-                raise ValueError('Incompatible shapes for broadcasting: {} and {}.'
-                                 .format(s0, s1))
-            new.append(max(s0, s1) if (s0 != 0 and s1 != 0) else 0)
-        shape = new
-    return tuple(shape)
+    """Shape that all `shapes` broadcast to (singleton axes stretch, missing axes are added on `side`);
+    ValueError when two sizes other than 1 disagree.  Same contract as interpol/utils.py:38-78."""
+    rank = max(map(len, shapes), default=0)
+
+    def aligned(shape):
+        fill = (1,) * (rank - len(shape))
+        return fill + tuple(shape) if side == 'left' else tuple(shape) + fill
+
+    out = []
+    for sizes in zip(*map(aligned, shapes)):
+        wide = sorted({int(n) for n in sizes if n != 1})
+        if len(wide) > 1:
+            raise ValueError('Incompatible shapes for broadcasting: {} and {}.'.format(wide[0], wide[1]))
+        out.append(wide[0] if wide else 1)
+    return tuple(out)
 
 
 def matvec(mat, vec, out=None):

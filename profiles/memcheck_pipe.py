@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Small forced-pipe problems for `compute-sanitizer --tool memcheck python profiles/memcheck_pipe.py`:
-every box mode (plain, folded x / y / z, zero-bound clipping, dft fix-up, split tiles) of the persistent kernels."""
+"""Small problems for `compute-sanitizer --tool memcheck python profiles/memcheck_pipe.py`: every box mode
+(plain, folded x / y / z, zero-bound clipping, dft fix-up, split tiles) of the persistent pull / grad kernels
+(forced) and of the boxed push / count kernels (default), f32 and f16, plus the fused backward and a
+displacement-field call."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'torch-interpol_b200')); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
@@ -25,5 +27,12 @@ for amp in (3.0, 25.0):
                 d = pp.grid_count(grid, list(shape), bound, [order], 2); seen.add(ib.last_kernel())
         finally:
             pp.flags = 0
+        # boxed push / count in 16-bit storage (order 5: the cfg 4 instantiation), fused backward, displacement mode
+        h = vol.half(); gh = grid.half()
+        pp.grid_push(h, gh, list(shape), bound, [5], 1); seen.add(ib.last_kernel())
+        pp.grid_count(gh, list(shape), bound, [5], 1); seen.add(ib.last_kernel())
+        vr = vol.clone().requires_grad_(); gr = grid.clone().requires_grad_()
+        pp.grid_pull_backward(torch.ones_like(vol), vr, gr, bound, [3], 1); seen.add(ib.last_kernel())
+        pp.grid_pull(vol, grid * 0.1, bound, [3], 1, True); seen.add(ib.last_kernel())
 torch.cuda.synchronize()
 print('ran', sorted(seen))

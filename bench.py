@@ -496,19 +496,30 @@ def main():
         from interpol_b200 import pushpull as pp
         bound = [BOUND_CODES[b] for b in spec['bound']]
         pulled = ops['pull']()
-        barrier()
-        a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
-        a.record(); full = ibd.gather_batch(pulled, spec['batch']); b_.record(); torch.cuda.synchronize()
-        t1 = torch.tensor([a.elapsed_time(b_)], dtype=torch.float64, device=device)
-        dist.all_reduce(t1, op=dist.ReduceOp.MAX)
         shp = list(vol.shape[2:])
         push1 = lambda i, g, s: pp.grid_push(i, g, s, bound, [spec['order']], 1)
-        barrier()
-        a.record(); shared = ibd.push_to_shared(push1, pulled[:1], grid[:1], shp); b_.record(); torch.cuda.synchronize()
-        t2 = torch.tensor([a.elapsed_time(b_)], dtype=torch.float64, device=device)
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        coll = {'gather_batch_ms': float(t1.item()), 'gather_batch_bytes': int(full.numel() * full.element_size()),
-                'push_to_shared_ms': float(t2.item()), 'push_to_shared_allreduce_bytes': int(shared.numel() * shared.element_size())}
+
+        def timed(fn, reps=3):
+            """max over ranks of the mean device time of `reps` calls, after one untimed call (the first collective
+            of a communicator pays NCCL's lazy channel set-up: 58 ms for a 28 MB all-reduce in r2d)"""
+            out = fn()
+            barrier()
+            a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b_.record(); torch.cuda.synchronize()
+            t_ = torch.tensor([a.elapsed_time(b_) / reps], dtype=torch.float64, device=device)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item()), out
+
+        t1, full = timed(lambda: ibd.gather_batch(pulled, spec['batch']))
+        t2, shared = timed(lambda: ibd.push_to_shared(push1, pulled[:1], grid[:1], shp))
+        # the splat alone, to separate the all-reduce from the kernel
+        t3, _ = timed(lambda: push1(pulled[:1], grid[:1], shp))
+        coll = {'gather_batch_ms': t1, 'gather_batch_bytes': int(full.numel() * full.element_size()),
+                'push_to_shared_ms': t2, 'push_to_shared_allreduce_bytes': int(shared.numel() * shared.element_size()),
+                'push_alone_ms': t3, 'timing': 'mean of 3 calls after 1 warm-up call, max over ranks'}
         del full, shared
 
     # ---- end-to-end through the public API with pinned host buffers ----------

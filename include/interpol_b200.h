@@ -70,6 +70,14 @@ enum {
     IB200_ERR_CUDA = -1000        /* IB200_ERR_CUDA - (int)cudaError_t */
 };
 
+/* storage type of the label maps of ib200_pull_labels (ib200_problem.reserved); `vol` and `out` share it */
+enum {
+    IB200_LABEL_I32 = 0,
+    IB200_LABEL_I64 = 1,
+    IB200_LABEL_U8 = 2,
+    IB200_LABEL_I16 = 3
+};
+
 /* behaviour switches (ib200_problem.flags) */
 enum {
     IB200_FLAG_NONE = 0,
@@ -103,7 +111,7 @@ typedef struct ib200_problem {
     int32_t bound[3];       /* per spatial axis, already padded (jit_utils.py:10-15) */
     int32_t order[3];       /* spline order 0..7 per spatial axis, already padded */
     uint32_t flags;         /* IB200_FLAG_* */
-    uint32_t reserved;
+    uint32_t reserved;      /* ib200_pull_labels: storage type of the label maps (IB200_LABEL_*); 0 elsewhere */
     int64_t batch;          /* B = max over operands (operands with B=1 use stride 0) */
     int64_t channels;       /* C */
     int64_t vol_shape[3];   /* spatial shape of the volume that is gathered from
@@ -175,12 +183,14 @@ IB200_API int ib200_spline_coeff(void *data, int32_t dtype, int64_t outer, int64
                        int64_t inner, int32_t bound, int32_t order,
                        int32_t device, void *stream);
 
-/* out (B, C, *pts_shape) int32 = label map `vol` (B, C, *vol_shape) int32 resampled at `grid`: for every
+/* out (B, C, *pts_shape) = label map `vol` (B, C, *vol_shape) resampled at `grid` (integer storage type
+ * p->reserved = IB200_LABEL_*, the same for both: torch's default int64 maps are read and written as they
+ * are, no int32 round trip): for every
  * point the label whose soft mask (vol == label) interpolates to the largest value (> 0, ties to the
  * smallest label, 0 when nothing is in bounds).  One pass replaces the loop over `input.unique()` of
  * interpol.grid_pull (interpol/api.py:194-205: one full pull per label).  Orders 0 / 1 per axis
  * (IB200_ERR_ORDER otherwise: higher orders prefilter the masks); p->dtype is the dtype of the GRID
- * (F32 / F64), vol_stride counts int32 elements. */
+ * (F32 / F64), vol_stride counts label elements. */
 IB200_API int ib200_pull_labels(const ib200_problem *p, const void *vol, const void *grid,
                       void *out, void *stream);
 

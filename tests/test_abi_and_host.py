@@ -254,7 +254,8 @@ def test_label_and_separable_dispatch_rules():
     assert api._labels_fused_ok(lab, g32, 1) and api._labels_fused_ok(lab.to(torch.uint8), g32, [0, 1])
     assert not api._labels_fused_ok(lab, g32, 3)                      # higher orders prefilter the masks
     assert not api._labels_fused_ok(lab, g32.half(), 1)               # 16-bit grids: label loop
-    assert not api._labels_fused_ok(lab + 2 ** 40, g32, 1)            # labels must fit in int32
+    assert api._labels_fused_ok(lab + 2 ** 40, g32, 1)                # int64 maps are read natively (any value)
+    assert api._labels_fused_ok(lab.to(torch.int8), g32, 0) and not api._labels_fused_ok(lab.bool(), g32, 0)
     x = torch.zeros(1, 1, 8, 8)
     ok_cuda = torch.cuda.is_available()
     assert rz._separable_ok(x, 2, {'bound': 'dct2'}) == ok_cuda

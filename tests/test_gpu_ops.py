@@ -424,6 +424,18 @@ def test_label_pull_fused_matches_label_loop(dim):
             else:
                 # identical except where two masks tie to rounding (both kernels sum the same terms in the same order)
                 assert (a != b).float().mean().item() <= 1e-4, (dim, dtype, order, bound, ex)
+    # int64 labels beyond the int32 range and int8 / int16 storage: read and written natively
+    big = (torch.randint(0, 4, [1, 1, *shape], generator=gen) * (2 ** 40) - 2 ** 41).cuda()
+    grid1 = smooth_grid(shape, gen, amp=2.0).contiguous().cuda()
+    a = ib.grid_pull(big, grid1, interpolation=1, bound='dct2', extrapolate=True)
+    assert ib.last_kernel() == 'pull_labels' and a.dtype == torch.int64
+    small = torch.div(big + 2 ** 41, 2 ** 40, rounding_mode='floor')
+    b = ib.grid_pull(small.to(torch.int16), grid1, interpolation=1, bound='dct2', extrapolate=True)
+    c = ib.grid_pull(small.to(torch.int8), grid1, interpolation=1, bound='dct2', extrapolate=True)
+    assert b.dtype == torch.int16 and c.dtype == torch.int8
+    # (dct2 + extrapolate: every point is reached by some mask, and the relabelling is monotone, so ties break alike)
+    assert torch.equal(torch.div(a + 2 ** 41, 2 ** 40, rounding_mode='floor'), b.long())
+    assert torch.equal(b.long(), c.long())
     # exact ties (up-sampling by 2 with linear weights: 0.5 / 0.5): the smallest label wins in both
     lab = torch.randint(0, 5, [1, 1, *shape], generator=gen).cuda()
     ident = ib.identity_grid(shape, device='cuda')[None] * 0.5

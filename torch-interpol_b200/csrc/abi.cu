@@ -267,7 +267,7 @@ static int run_labels(const ib200_problem *p, const void *vol, const void *grid,
     if (!vol || !grid || !out) return IB200_ERR_NULL;
     DeviceGuard guard(p->device);
     if (!guard.ok) return IB200_ERR_CUDA - (int)cudaErrorInvalidDevice;
-    return launch_pull_labels(kp, p->dtype, vol, grid, out, (cudaStream_t)stream);
+    return launch_pull_labels(kp, p->dtype, (int)p->reserved, vol, grid, out, (cudaStream_t)stream);
 }
 }  // namespace ib200
 

@@ -121,7 +121,7 @@ int launch_resample(const KParams &kp, int dtype, const void *in, void *out, con
                     i64 n_out, i64 inner, int order, int bound, int extrapolate, cudaStream_t stream);
 int launch_resample_adjoint(const KParams &kp, int dtype, const void *in, void *out, const void *coords, i64 outer, i64 n_in,
                             i64 n_out, i64 inner, int order, int bound, int extrapolate, cudaStream_t stream);
-int launch_pull_labels(const KParams &kp, int grid_dtype, const void *vol, const void *grid, void *out, cudaStream_t stream);
+int launch_pull_labels(const KParams &kp, int grid_dtype, int label_type, const void *vol, const void *grid, void *out, cudaStream_t stream);
 
 enum { OP_PULL = 0, OP_GRAD = 1, OP_HESS = 2, OP_PULL_BWD_GRID = 3, OP_GRAD_BWD_GRID = 4 };
 enum { OP_PUSH = 0, OP_COUNT = 1, OP_PUSHGRAD = 2 };

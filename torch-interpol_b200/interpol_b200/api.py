@@ -308,19 +308,14 @@ LABELS_FUSED = True      # False: always loop over the labels like the reference
 
 
 def _labels_fused_ok(input, grid, interpolation):
-    """The fused label kernel covers orders 0 / 1 (no prefilter involved), float32 / float64 grids, and
-    labels that fit in int32."""
+    """The fused label kernel covers orders 0 / 1 (no prefilter involved), float32 / float64 grids and the integer
+    storage types it reads natively (int8 maps are widened to int16)."""
     if not LABELS_FUSED or grid.dtype not in (torch.float32, torch.float64) or input.numel() == 0:
         return False
     from .autograd import inter_to_nitorch, make_list
     if any(o > 1 for o in inter_to_nitorch(make_list(interpolation), as_type='int')):
         return False
-    if input.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32):
-        return True
-    if input.dtype == torch.int64:
-        lo, hi = input.amin().item(), input.amax().item()
-        return -2 ** 31 <= lo and hi < 2 ** 31
-    return False
+    return input.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64)
 
 
 def _pull_labels_by_mask(labels, grid, interpolation, bound, extrapolate, prefilter, displacement):
@@ -379,7 +374,8 @@ def grid_pull(input, grid, interpolation='linear', bound='zero',
         from .autograd import _options
         from . import pushpull as _pp
         bnd, order, extr = _options(interpolation, bound, extrapolate)
-        out = _pp.grid_pull_labels(input.to(torch.int32), grid, bnd, order, extr, displacement).to(input.dtype)
+        stored = input.to(torch.int16) if input.dtype == torch.int8 else input
+        out = _pp.grid_pull_labels(stored, grid, bnd, order, extr, displacement).to(input.dtype)
     else:
         out = _pull_labels_by_mask(input, grid, interpolation, bound, extrapolate, prefilter, displacement)
     return back(layout.restore(out))

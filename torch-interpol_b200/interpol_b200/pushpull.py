@@ -153,26 +153,31 @@ def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gou
     return out
 
 
+LABEL_TYPES = {torch.int32: 0, torch.int64: 1, torch.uint8: 2, torch.int16: 3}      # IB200_LABEL_*
+
+
 def grid_pull_labels(inp, grid, bound: List[int], interpolation: List[int], extrapolate: int, displacement=False):
-    """(B, C, *spatial_in) int32 label map, (B, *spatial_out, D) float32/64 grid -> (B, C, *spatial_out) int32:
-    per point, the label whose soft mask interpolates to the largest value (orders 0 / 1).  One pass instead of
-    the loop over `input.unique()` of interpol/api.py:194-205."""
+    """(B, C, *spatial_in) integer label map (int32 / int64 / uint8 / int16, read as stored), (B, *spatial_out, D)
+    float32/64 grid -> (B, C, *spatial_out) of the same integer type: per point, the label whose soft mask
+    interpolates to the largest value (orders 0 / 1).  One pass instead of the loop over `input.unique()` of
+    interpol/api.py:194-205."""
     _lib.require_cuda(inp, grid)
     dim = grid.shape[-1]
     if grid.dim() != dim + 2 or inp.dim() != dim + 2:
         raise ValueError('expected inp (B, C, *spatial) and grid (B, *spatial, D)')
-    if inp.dtype != torch.int32 or grid.dtype not in (torch.float32, torch.float64):
-        raise TypeError('grid_pull_labels: int32 labels and a float32 / float64 grid expected')
+    if inp.dtype not in LABEL_TYPES or grid.dtype not in (torch.float32, torch.float64):
+        raise TypeError('grid_pull_labels: int32 / int64 / uint8 / int16 labels and a float32 / float64 grid expected')
     batch = _batch(inp, grid)
     channels = inp.shape[1]
     oshape = grid.shape[1:-1]
     p = _problem(dim, grid.dtype, grid.device, bound, interpolation, extrapolate, batch, channels, inp.shape[2:], oshape,
                  displacement)
+    p.reserved = LABEL_TYPES[inp.dtype]
     _set_vol(p, inp, batch, dim)
     _set_grid(p, grid, batch, dim)
     L = _lib.lib()
     with torch.cuda.device(grid.device):
-        out = torch.empty([batch, channels, *oshape], dtype=torch.int32, device=grid.device)
+        out = torch.empty([batch, channels, *oshape], dtype=inp.dtype, device=grid.device)
         st = L.ib200_pull_labels(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid), _lib.ptr(out), _lib.stream_ptr(grid.device))
     _lib.check(st)
     return out

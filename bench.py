@@ -91,18 +91,29 @@ class ClockSampler(threading.Thread):
         n = self.nvml
         masks = [getattr(n, 'nvmlClocksEventReasonHwSlowdown', 0x8), getattr(n, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
                  getattr(n, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), getattr(n, 'nvmlClocksEventReasonSwPowerCap', 0x4)]
+        self.masks = masks
         while not self.stop_flag:
-            try:
-                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                try:
-                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:
-                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                if self.armed:
-                    self.samples.append((mhz, [bool(r & m) for m in masks]))
-            except Exception:
-                pass
+            self.sample_now()
             time.sleep(0.002)
+
+    def sample_now(self):
+        """One NVML query, kept if the timed region is open.  Also called by the main thread right after it has
+        queued the timed steps (the GPU is then busy with them): an NVML call can take several ms, and a short
+        timed region could otherwise end before the polling thread completes a single query."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            armed = self.armed
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            if armed:
+                self.samples.append((mhz, [bool(r & m) for m in getattr(self, 'masks', [0x8, 0x40, 0x20, 0x4])]))
+        except Exception:
+            pass
 
     def finish(self):
         self.stop_flag = True
@@ -476,6 +487,8 @@ def main():
         for i, o in enumerate(names):
             ops[o]()
             ev[k][i + 1].record()
+    if rank == 0:
+        sampler.sample_now()                # the timed steps are queued and running
     barrier()
     sampler.armed = False
     launches = ib.launch_count() - launches0
@@ -670,7 +683,8 @@ def run_e2e(spec, vol, grid, args, dist, device, world, total_units):
     return {'value': total_units / e2e_s / 1e6, 'unit': 'Mvoxels/s', 'h2d_bytes_per_step': int(h2d),
             'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_s * 1e3, 'steps': steps,
             'api': 'interpol_b200.%s on pinned CPU tensors inside interpol_b200.stage_scope() (one upload per '
-                   'distinct host tensor per step; every result copied back)' % ' / '.join(
+                   'distinct host tensor per step; the lattice of a pull / grad goes up in slabs so that upload, kernel '
+                   'and download overlap; every result copied back)' % ' / '.join(
                        'spline_coeff_nd' if o == 'coeff' else 'grid_' + o for o in names)}
 
 

@@ -9,6 +9,8 @@
 //           voxel m; 16 consecutive voxels per warp instruction, span 15 s + 4 <= 32 words up to s = 1.87
 //   MODE 2  (push only) k-split with the 16 voxels of an instruction taken at stride 2 along z (even voxels,
 //           then odd voxels): no two lanes share an accumulator word down to s = 0.5
+//   MODE 3  (push only) one lane per source, warp-aggregated: a source in the same cell as its lower z-neighbour
+//           rides along with it (4 SHFL, second weight set in the leader) instead of colliding on its 64 words
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -151,6 +153,40 @@ __global__ void __launch_bounds__(NT, 1) push_lab(float stretch, float shear, in
                             atomicAdd(rk + i * PLANE + j * BZ + k, __float_as_int(fmaf(vij, wz[k], kMagic)) - kMagicBits);
                     }
                 }
+            } else if (MODE == 3) {
+                // warp-aggregated: a source whose support starts in the same cell as its lower z-neighbour's hands its
+                // value and coordinates to that neighbour (4 SHFL) and issues no atomics; the neighbour adds both
+                // contributions before the float -> fixed conversion
+                const float *gp = gt + (r * TZ + lane) * 3;
+                const float c0 = gp[0], c1 = gp[1], c2 = gp[2];
+                const float f0 = floorf(c0 - 1.f), f1 = floorf(c1 - 1.f), f2 = floorf(c2 - 1.f);
+                const int cell = (int)f0 * PLANE + (int)f1 * BZ + (int)f2;
+                const int pcell = __shfl_up_sync(0xffffffffu, cell, 1);
+                const bool sp = lane > 0 && pcell == cell;
+                const bool spp = __shfl_up_sync(0xffffffffu, (int)sp, 1) != 0;
+                const bool follower = sp && !(lane > 1 && spp);
+                const bool lead2 = __shfl_down_sync(0xffffffffu, (int)follower, 1) != 0 && lane < 31;
+                const float val = vals[r * TZ + lane] * scale;
+                const float d0 = __shfl_down_sync(0xffffffffu, c0, 1), d1 = __shfl_down_sync(0xffffffffu, c1, 1),
+                            d2 = __shfl_down_sync(0xffffffffu, c2, 1);
+                const float vb = lead2 ? __shfl_down_sync(0xffffffffu, val, 1) : 0.f * __shfl_down_sync(0xffffffffu, val, 1);
+                if (!follower) {
+                    float wx[4], wy[4], wz[4], ux[4], uy[4], uz[4];
+                    w3(c0 - f0, wx); w3(c1 - f1, wy); w3(c2 - f2, wz);
+                    w3(lead2 ? d0 - f0 : 1.5f, ux); w3(lead2 ? d1 - f1 : 1.5f, uy); w3(lead2 ? d2 - f2 : 1.5f, uz);
+                    int *rk = box + cell;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float vi = val * wx[i], ui = vb * ux[i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float vij = vi * wy[j], uij = ui * uy[j];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                atomicAdd(rk + i * PLANE + j * BZ + k, __float_as_int(fmaf(vij, wz[k], fmaf(uij, uz[k], kMagic))) - kMagicBits);
+                        }
+                    }
+                }
             } else {
                 const int v = lane >> 1, h = lane & 1;
 #pragma unroll 1
@@ -198,6 +234,7 @@ int main() {
     CK(cudaFuncSetAttribute(push_lab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(push_lab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(push_lab<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(push_lab<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     auto report = [&](const char *name, float s, float sh) {
         CK(cudaDeviceSynchronize());
         long long h[blocks]; CK(cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost));
@@ -221,6 +258,8 @@ int main() {
             report("push  k-split adjacent", s, sh);
             for (int rep = 0; rep < 2; ++rep) push_lab<2><<<blocks, NT, smem>>>(s, sh, ntiles, d_out, d_cyc);
             report("push  k-split stride 2", s, sh);
+            for (int rep = 0; rep < 2; ++rep) push_lab<3><<<blocks, NT, smem>>>(s, sh, ntiles, d_out, d_cyc);
+            report("push  warp-aggregated neighbours", s, sh);
         }
     return 0;
 }

@@ -46,7 +46,7 @@ def main(ncases=None, seed=None):
             if shape[0] * shape[1] * shape[2] >= 32768:
                 break
         vshape = tuple(rng.randint(5, 60) for _ in range(3))
-        B, C = rng.choice([1, 1, 2]), rng.choice([1, 1, 2, 3])
+        B, C = rng.choice([1, 1, 2]), rng.choice([1, 1, 2, 3, 4, 4])
         order = rng.choice([1, 1, 2, 3, 3, 3, 4, 5, 6, 7])
         bound = [rng.randint(0, 6) for _ in range(3)] if rng.random() < 0.7 else [rng.randint(0, 6)]
         ex = rng.choice([0, 1, 1, 2])
@@ -89,6 +89,8 @@ def main(ncases=None, seed=None):
         # (scatters: the generic arm accumulates with float32 atomics in arrival order -- its own noise is ~1e-5 when a
         # few hundred sources land on one voxel; case 125 of seed 1 is 4.6e-6 (boxed) / 7.8e-6 (generic) off the oracle)
         tol = (2e-2 if half else (4e-5 if op in ('push', 'count') else 2e-5)) * max(scale, 1e-30)
+        if half:
+            tol = max(tol, 4 * 5.96e-8)          # results that vanish: a few float16 subnormal quanta
         # pile-ups (a folding deformation splatted through `replicate` onto one face: 1e5 sources on one voxel):
         # float32 accumulation drops increments below half an ulp of the running sum in BOTH kernels and in the
         # reference (each is ~2 % off the float64 oracle there, profiles/diag/fuzz_check.py); they only agree loosely

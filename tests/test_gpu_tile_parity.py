@@ -375,3 +375,30 @@ def test_displacement_mode_equals_identity_plus_grid(dim, shape):
     ib.grid_pull(v2, g2, interpolation=3, bound='dct2', extrapolate=True).backward(gout)
     assert rel_err(to_np(v1.grad), to_np(v2.grad)) <= 2e-6
     assert rel_err(to_np(d1.grad), to_np(g2.grad)) <= 2e-6
+
+
+# ------------------------------------------------- channel-interleaved boxes --
+
+@pytest.mark.parametrize('channels', [4, 8])
+@pytest.mark.parametrize('extrapolate', [1, 0, 2])
+@pytest.mark.parametrize('order', [1, 2, 3])
+def test_interleaved_channel_boxes_vs_oracle(order, extrapolate, channels):
+    """float32 volumes with a multiple of 4 channels: pull / grad through the channel-interleaved boxes (one LDS.128
+    per node for four channels, `*_c4` kernels), every bound, partial tiles, points outside the field of view; a steep
+    deformation sends some groups through the incoherent fallback of the same kernel.  Strided (padded) volumes too."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    for amp, bound in ((3.0, [(order + extrapolate) % 7, (order + 2) % 7, (order + 4 + extrapolate) % 7]), (40.0, [3]), (3.0, [0])):
+        vol, _, grid = _case(order, 900 + 10 * order + extrapolate + channels, B=2, C=channels, amp=amp)
+        grid = _off_threshold(grid, VSHAPE)
+        v64, g64 = vol.double().numpy(), grid.double().numpy()
+        big = torch.zeros([2, channels, VSHAPE[0], VSHAPE[1], VSHAPE[2] + 3])
+        big[..., :VSHAPE[2]] = vol
+        for v_dev in (vol.cuda(), big.cuda()[..., :VSHAPE[2]]):
+            got = pp.grid_pull(v_dev, grid.cuda(), bound, [order], extrapolate)
+            assert ib.last_kernel().startswith('pull_tile3d') and ib.last_kernel().endswith('_c4'), ib.last_kernel()
+            assert rel_err(to_np(got), oracle.grid_pull(v64, g64, bound, [order], extrapolate)) <= 1e-5
+            got = pp.grid_grad(v_dev, grid.cuda(), bound, [order], extrapolate)
+            assert ib.last_kernel().startswith('grad_tile3d') and ib.last_kernel().endswith('_c4'), ib.last_kernel()
+            assert rel_err(to_np(got), oracle.grid_grad(v64, g64, bound, [order], extrapolate)) <= 1e-5

@@ -27,7 +27,13 @@
 
 namespace ib200 {
 
-template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MINB>
+// IL = 4: channel-interleaved variant for float32 volumes with a multiple of 4 channels.  The box holds one float4 per
+// voxel (channels c .. c+3, gathered from the four channel planes while staging), so a tap is ONE LDS.128 for four
+// channels and coordinates, weights and row addresses are evaluated once per point instead of once per point and
+// channel: 64 + 4 * 44 instructions per point for the taps of four channels instead of 4 * (64 + 84).  A quarter warp
+// (8 lanes, consecutive z) reads 8 consecutive float4 = all 32 banks, so rows need no padding and lanes on different
+// rows never collide.
+template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MINB, int IL>
 __global__ void __launch_bounds__(NT, MINB)
 pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol,
                    const T *__restrict__ grid, const T *__restrict__ gout, T *__restrict__ out, const int cap, const int vec_ok) {
@@ -41,6 +47,7 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
     constexpr bool BWD = (OP == OP_PULL_BWD_GRID);
     constexpr int UI = ORDER <= 3 ? W : 1, UJ = ORDER <= 5 ? W : 1;   // keep the code of high orders compact
     static_assert(NT == TY * TZ, "one thread per (y, z) column of the tile; x-planes are looped");
+    static_assert(IL == 1 || (IL == 4 && sizeof(T) == 4 && OP != OP_PULL_BWD_GRID), "interleaved boxes: float32 pull / grad");
     static_assert(TZ % 4 == 0, "z rows are staged 16 bytes at a time");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);                  // [cap] input box
@@ -68,7 +75,8 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
     cp_async_wait_all();
     __syncthreads();
     tile_add_identity<T, TX, NT>(kp, gtile, x0, y0 + ly, z0 + lz);
-    plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, cap, 0.f, TZ == 16 ? 16 : 32);
+    plan_from_coords<T, ORDER, TX, NT>(kp, gtile, col_ok, x0, red, pb, geoms, nsub_p, IL == 4 ? cap / 4 : cap, 0.f,
+                                       IL == 4 ? 4 : (TZ == 16 ? 16 : 32));
     const int nsub = *nsub_p;
     const int per = TX / nsub;
 
@@ -87,11 +95,127 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
             continue;
         }
         if (g.fits) { __syncthreads(); build_tables<NT>(kp, g, idx_tab, sgn_tab); }
-        for (i64 c = 0; c < kp.channels; ++c) {
+        for (i64 c = 0; c < kp.channels; c += IL) {
             const T *src = vol + b * kp.vol_sb + c * kp.vol_sc;
             T *dst = out + (BWD ? b : b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1);
             const T *gm = BWD ? gout + b * kp.img_sb + c * kp.img_sc : nullptr;
-            if (g.fits) {
+            if constexpr (IL == 4) {
+              if (g.fits) {
+                // ---- 3'. stage the box: one voxel (float4 = four channels) per thread and step ----
+                __syncthreads();          // previous taps done, tables visible
+                float4 *tile4 = reinterpret_cast<float4 *>(tile);
+                const int e2 = g.ext[2];
+                const int total = g.ext[0] * g.ext[1] * e2;
+                const unsigned inv_e2 = make_inv(e2);
+                const i64 sc = kp.vol_sc;
+                const int rot = (threadIdx.x >> 3) & 3;
+                // (a warp per box row -- row base and sign once per row -- was measured slower: fewer copies in flight)
+#pragma unroll 4
+                for (int q = threadIdx.x; q < total; q += NT) {
+                    const int r = fast_div(q, inv_e2), zz = q - r * e2;
+                    const int a = fast_div(r, g.inv_e1), bb = r - a * g.ext[1];
+                    const float sg = sgn_tab[a] * sgn_tab[kMaxExt + bb] * sgn_tab[2 * kMaxExt + zz];
+                    const float *sp = src + idx_tab[a] + idx_tab[kMaxExt + bb] + idx_tab[2 * kMaxExt + zz];
+                    float4 *td = tile4 + a * g.sxy + bb * g.sz + zz;
+                    if (sg == 1.f) {
+                        // The common case travels asynchronously, one 4-byte copy per channel plane.  Lane v writes word
+                        // 4 v + ch of 128 consecutive words: with the same ch for all lanes the 32 words sit in 8 banks
+                        // (4-way conflict, measured: 49 M wavefronts for 19 M ideal).  Copy m of lane v takes channel
+                        // (m + v / 8) mod 4 instead: banks 4 (v mod 8) + ch are all distinct, and every group of 8 lanes
+                        // still reads 32 contiguous bytes of one channel plane (32 M wavefronts).
+                        float *tf = reinterpret_cast<float *>(td);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int ch = (m + rot) & 3;
+                            cp_async4(tf + ch, sp + ch * sc);
+                        }
+                    } else {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (sg != 0.f) v = make_float4(sg * __ldg(sp), sg * __ldg(sp + sc), sg * __ldg(sp + 2 * sc), sg * __ldg(sp + 3 * sc));
+                        *td = v;
+                    }
+                }
+                cp_async_wait_all();
+                __syncthreads();
+                // ---- 4'. taps: one LDS.128 per node, packed FFMA2 over the channel pairs ----
+#pragma unroll 1
+                for (int p = s * per; p < (s + 1) * per; ++p) {
+                    if (!(col_ok && x0 + p < kp.pts_n[0])) continue;
+                    const T *gp = gtile + (p * NT + threadIdx.x) * 3;
+                    const float cc[3] = {(float)gp[0], (float)gp[1], (float)gp[2]};
+                    const float f0 = floorf(cc[0] - 0.5f * (ORDER - 1)), f1 = floorf(cc[1] - 0.5f * (ORDER - 1)),
+                                f2 = floorf(cc[2] - 0.5f * (ORDER - 1));
+                    const bool actp = inbounds<float, 3>(kp, cc) && fabsf(f0) < 4e18f && fabsf(f1) < 4e18f && fabsf(f2) < 4e18f;
+                    // (lo, hi) = channels (c, c+1), (c+2, c+3); value / d-dx / d-dy / d-dz accumulators
+                    float2 a_lo = make_float2(0.f, 0.f), a_hi = a_lo, x_lo = a_lo, x_hi = a_lo, y_lo = a_lo, y_hi = a_lo, z_lo = a_lo, z_hi = a_lo;
+                    if (actp) {
+                        float wx[W], wy[W], wz[W], gx[W], gy[W], gz[W];
+                        fast_weights<ORDER>(cc[0] - f0, wx);
+                        fast_weights<ORDER>(cc[1] - f1, wy);
+                        fast_weights<ORDER>(cc[2] - f2, wz);
+                        if (GRAD) {
+                            fast_dweights<ORDER>(cc[0] - f0, gx);
+                            fast_dweights<ORDER>(cc[1] - f1, gy);
+                            fast_dweights<ORDER>(cc[2] - f2, gz);
+                        }
+                        const float4 *ri = tile4 + ((int)f0 - g.lo[0]) * g.sxy + ((int)f1 - g.lo[1]) * g.sz + ((int)f2 - g.lo[2]);
+#pragma unroll
+                        for (int i = 0; i < W; ++i) {
+                            const float4 *rj = ri;
+                            float2 s00l = make_float2(0.f, 0.f), s00h = s00l, s10l = s00l, s10h = s00l, s01l = s00l, s01h = s00l;
+#pragma unroll
+                            for (int j = 0; j < W; ++j) {
+                                float2 t0l = make_float2(0.f, 0.f), t0h = t0l, t1l = t0l, t1h = t0l;
+#pragma unroll
+                                for (int k = 0; k < W; ++k) {
+                                    const float4 v = rj[k];
+                                    const float2 wk = make_float2(wz[k], wz[k]);
+                                    t0l = __ffma2_rn(wk, make_float2(v.x, v.y), t0l);
+                                    t0h = __ffma2_rn(wk, make_float2(v.z, v.w), t0h);
+                                    if (GRAD) {
+                                        const float2 gk = make_float2(gz[k], gz[k]);
+                                        t1l = __ffma2_rn(gk, make_float2(v.x, v.y), t1l);
+                                        t1h = __ffma2_rn(gk, make_float2(v.z, v.w), t1h);
+                                    }
+                                }
+                                const float2 wj = make_float2(wy[j], wy[j]);
+                                s00l = __ffma2_rn(wj, t0l, s00l); s00h = __ffma2_rn(wj, t0h, s00h);
+                                if (GRAD) {
+                                    const float2 gj = make_float2(gy[j], gy[j]);
+                                    s10l = __ffma2_rn(gj, t0l, s10l); s10h = __ffma2_rn(gj, t0h, s10h);
+                                    s01l = __ffma2_rn(wj, t1l, s01l); s01h = __ffma2_rn(wj, t1h, s01h);
+                                }
+                                rj += g.sz;
+                            }
+                            const float2 wi = make_float2(wx[i], wx[i]);
+                            if (!GRAD) { a_lo = __ffma2_rn(wi, s00l, a_lo); a_hi = __ffma2_rn(wi, s00h, a_hi); }
+                            else {
+                                const float2 gi = make_float2(gx[i], gx[i]);
+                                x_lo = __ffma2_rn(gi, s00l, x_lo); x_hi = __ffma2_rn(gi, s00h, x_hi);
+                                y_lo = __ffma2_rn(wi, s10l, y_lo); y_hi = __ffma2_rn(wi, s10h, y_hi);
+                                z_lo = __ffma2_rn(wi, s01l, z_lo); z_hi = __ffma2_rn(wi, s01h, z_hi);
+                            }
+                            ri += g.sxy;
+                        }
+                    }
+                    const i64 r = ((i64)(x0 + p) * kp.pts_n[1] + (y0 + ly)) * kp.pts_n[2] + (z0 + lz);
+                    const i64 cs = kp.pts_total * (GRAD ? 3 : 1);
+                    if (!GRAD) {
+                        dst[r] = a_lo.x; dst[cs + r] = a_lo.y; dst[2 * cs + r] = a_hi.x; dst[3 * cs + r] = a_hi.y;
+                    } else {
+                        const float gx4[4] = {x_lo.x, x_lo.y, x_hi.x, x_hi.y}, gy4[4] = {y_lo.x, y_lo.y, y_hi.x, y_hi.y},
+                                    gz4[4] = {z_lo.x, z_lo.y, z_hi.x, z_hi.y};
+#pragma unroll
+                        for (int cg = 0; cg < 4; ++cg) {
+                            T *d = dst + cg * cs + r * 3;
+                            d[0] = gx4[cg]; d[1] = gy4[cg]; d[2] = gz4[cg];
+                        }
+                    }
+                }
+                continue;                 // next group of four channels
+              }
+            }
+            if (IL == 1 && g.fits) {
                 // ---- 3. stage the box, one 4-word vector per thread -------------------
                 // x / y folding comes from the per-axis tables (row base, row sign).  A
                 // vector whose 4 source voxels lie inside the volume along z on a row of
@@ -173,7 +297,11 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
                     else { Traits<T>::store(dst + r * 3, ax_); Traits<T>::store(dst + r * 3 + 1, ay_); Traits<T>::store(dst + r * 3 + 2, az_); }
                 }
             } else {
-                // ---- incoherent group: direct global gathers --------------------------
+                // ---- incoherent group: direct global gathers (channel by channel) ------
+#pragma unroll 1
+              for (int cg = 0; cg < IL; ++cg) {
+                const T *src = vol + b * kp.vol_sb + (c + cg) * kp.vol_sc;
+                T *dst = out + (BWD ? b : b * kp.channels + c + cg) * kp.pts_total * (GRAD ? 3 : 1);
 #pragma unroll 1
                 for (int p = s * per; p < (s + 1) * per; ++p) {
                     if (!(col_ok && x0 + p < kp.pts_n[0])) continue;
@@ -215,6 +343,7 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
                     if (!GRAD) Traits<T>::store(dst + r, acc);
                     else { Traits<T>::store(dst + r * 3, ag[0]); Traits<T>::store(dst + r * 3 + 1, ag[1]); Traits<T>::store(dst + r * 3 + 2, ag[2]); }
                 }
+              }
             }
         }
     }
@@ -222,7 +351,7 @@ pull_tile3d_kernel(const __grid_constant__ KParams kp, const T *__restrict__ vol
 
 // ---------------------------------------------------------------- launch --
 
-template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MINB>
+template <typename T, int ORDER, int OP, int TX, int TY, int TZ, int NT, int MINB, int IL = 1>
 static int launch_pull_tile_cfg(const KParams &kp, const void *vol, const void *grid, const void *gout, void *out, cudaStream_t stream,
                                 size_t smem_total) {
     const size_t fixed = (size_t)TX * TY * TZ * 3 * sizeof(T) + 3 * kMaxExt * (sizeof(int) + sizeof(float)) +
@@ -236,11 +365,12 @@ static int launch_pull_tile_cfg(const KParams &kp, const void *vol, const void *
     const bool vec_ok = ((uintptr_t)vol % 16 == 0) && ((uintptr_t)grid % 16 == 0) &&
                         (kp.vol_s[0] % ev == 0) && (kp.vol_s[1] % ev == 0) && (kp.vol_sb % ev == 0) && (kp.vol_sc % ev == 0) &&
                         ((kp.pts_n[2] * 3) % ev == 0) && (kp.grid_sb % ev == 0);
-    auto kern = pull_tile3d_kernel<T, ORDER, OP, TX, TY, TZ, NT, MINB>;
+    auto kern = pull_tile3d_kernel<T, ORDER, OP, TX, TY, TZ, NT, MINB, IL>;
     IB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
     kern<<<(unsigned)ntiles, NT, smem_total, stream>>>(kp, (const T *)vol, (const T *)grid, (const T *)gout, (T *)out, cap, vec_ok ? 1 : 0);
     static thread_local char name[64];
-    snprintf(name, sizeof(name), "%s_tile3d_o%d_%dx%dx%d", OP == OP_GRAD ? "grad" : OP == OP_PULL_BWD_GRID ? "pullbwd" : "pull", ORDER, TX, TY, TZ);
+    snprintf(name, sizeof(name), "%s_tile3d_o%d_%dx%dx%d%s", OP == OP_GRAD ? "grad" : OP == OP_PULL_BWD_GRID ? "pullbwd" : "pull", ORDER, TX, TY, TZ,
+             IL == 4 ? "_c4" : "");
     note_launch(name);
     IB200_CUDA_CHECK(cudaGetLastError());
     return 1;
@@ -261,6 +391,11 @@ static int launch_pull_tile(const KParams &kp, const void *vol, const void *grid
         }
     }
 #endif
+    // float32 volumes with a multiple of 4 channels: channel-interleaved boxes (see the kernel's header)
+    if constexpr (sizeof(T) == 4 && OP != OP_PULL_BWD_GRID && ORDER <= 3) {
+        if (kp.channels >= 4 && kp.channels % 4 == 0 && !(kp.flags & IB200_FLAG_NO_PIPE))
+            return launch_pull_tile_cfg<T, ORDER, OP, 8, 8, 16, 128, 3, 4>(kp, vol, grid, gout, out, stream, 74 * 1024);   // (2 CTAs x 110 KB: 5-20 % slower)
+    }
     return launch_pull_tile_cfg<T, ORDER, OP, 8, 8, 32, 256, 2>(kp, vol, grid, gout, out, stream, 110 * 1024);
 }
 

@@ -86,8 +86,9 @@ enum {
     /* reproduce the reference's sign error for d/dx of the order-1 spline on an
      * axis of a mixed-order call (splines.py:96-97); default is the true derivative */
     IB200_FLAG_REF_LINEAR_GRAD_SIGN = 1u << 1,
-    /* never take the persistent warp-specialised kernels (fall back to the one-tile-per-CTA
-     * tiled kernels; A/B testing, profiling) */
+    /* never take the persistent warp-specialised pull / grad, the boxed push / count or the
+     * channel-interleaved tile kernels (fall back to the round-1 one-tile-per-CTA tiled kernels;
+     * A/B testing, profiling) */
     IB200_FLAG_NO_PIPE = 1u << 2,
     /* take the persistent kernels even for problems too small to amortise their ramp-up (tests) */
     IB200_FLAG_FORCE_PIPE = 1u << 3,

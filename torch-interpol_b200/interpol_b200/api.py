@@ -13,6 +13,7 @@ import threading
 import torch
 
 from .utils import expanded_shape, matvec, meshgrid_ij
+from . import pushpull as _pp
 from .autograd import (GridPull, GridPush, GridCount, GridGrad,
                        SplineCoeff, SplineCoeffND)
 
@@ -284,6 +285,13 @@ class _Layout:
 
     def __init__(self, grid, volume=None, splat=False):
         self.dim = dim = grid.shape[-1]
+        self.canonical = False
+        if volume is not None and grid.dim() == dim + 2 and volume.dim() == dim + 2 and grid.shape[0] == volume.shape[0] \
+                and (not splat or grid.shape[1:-1] == volume.shape[2:]):
+            # already (B, C, *spatial) / (B, *spatial, D) with one batch: nothing to expand, reshape or restore
+            # (15 us of view construction per call otherwise -- it shows at 64^3)
+            self.canonical, self.grid, self.volume = True, grid, volume
+            return
         lattice, lead_g = tuple(grid.shape[-dim - 1:-1]), tuple(grid.shape[:-dim - 1])
         if volume is None:                           # count: the output has one channel iff there is a batch
             self.lead, self.channels = lead_g, ([1] if lead_g else [])
@@ -300,8 +308,20 @@ class _Layout:
 
     def restore(self, out, features=0):
         """(B, C, *spatial[, features]) back to the caller's leading axes."""
+        if self.canonical:
+            return out
         tail = out.shape[2:]
         return out.reshape([*self.lead, *self.channels, *tail])
+
+
+def _apply(function, kernel, tensors, shape, interpolation, bound, extrapolate, displacement):
+    """`function.apply(...)`, or the kernel behind it called directly when neither autograd (no tensor requires a
+    gradient, or grad mode is off) nor autocast has anything to do: the Function machinery costs ~12 us per call."""
+    needs_graph = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+    if needs_graph or torch.is_autocast_enabled():
+        return function.apply(*tensors, *shape, interpolation, bound, extrapolate, displacement)
+    from .autograd import _options
+    return kernel(*tensors, *shape, *_options(interpolation, bound, extrapolate), bool(displacement))
 
 
 LABELS_FUSED = True      # False: always loop over the labels like the reference (A/B testing)
@@ -368,11 +388,10 @@ def grid_pull(input, grid, interpolation='linear', bound='zero',
     if input.dtype.is_floating_point:
         if prefilter:
             input = spline_coeff_nd(input, interpolation=interpolation, bound=bound, dim=dim)
-        out = GridPull.apply(input, grid, interpolation, bound, extrapolate, displacement)
+        out = _apply(GridPull, _pp.grid_pull, (input, grid), (), interpolation, bound, extrapolate, displacement)
     elif _labels_fused_ok(input, grid, interpolation):
         # one pass: every point looks for the arg-max among the labels of its own (order+1)^dim nodes
         from .autograd import _options
-        from . import pushpull as _pp
         bnd, order, extr = _options(interpolation, bound, extrapolate)
         stored = input.to(torch.int16) if input.dtype == torch.int8 else input
         out = _pp.grid_pull_labels(stored, grid, bnd, order, extr, displacement).to(input.dtype)
@@ -393,7 +412,7 @@ def grid_push(input, grid, shape=None, interpolation='linear', bound='zero',
     layout = _Layout(grid, input, splat=True)
     if shape is None:
         shape = tuple(layout.volume.shape[2:])
-    out = GridPush.apply(layout.volume, layout.grid, shape, interpolation, bound, extrapolate, displacement)
+    out = _apply(GridPush, _pp.grid_push, (layout.volume, layout.grid), (shape,), interpolation, bound, extrapolate, displacement)
     if prefilter:
         out = spline_coeff_nd(out, interpolation=interpolation, bound=bound, dim=layout.dim, inplace=True)
     return back(layout.restore(out))
@@ -407,7 +426,7 @@ def grid_count(grid, shape=None, interpolation='linear', bound='zero',
     """
     (grid,), back = _stage(grid)
     layout = _Layout(grid)
-    out = GridCount.apply(layout.grid, shape, interpolation, bound, extrapolate, displacement)
+    out = _apply(GridCount, _pp.grid_count, (layout.grid,), (shape,), interpolation, bound, extrapolate, displacement)
     return back(layout.restore(out))
 
 
@@ -426,7 +445,7 @@ def grid_grad(input, grid, interpolation='linear', bound='zero',
     input = layout.volume
     if prefilter:
         input = spline_coeff_nd(input, interpolation, bound, layout.dim)
-    out = GridGrad.apply(input, layout.grid, interpolation, bound, extrapolate, displacement)
+    out = _apply(GridGrad, _pp.grid_grad, (input, layout.grid), (), interpolation, bound, extrapolate, displacement)
     return back(layout.restore(out))
 
 

@@ -19,7 +19,7 @@ def _filter_axis_(x, bound: int, order: int, axis: int):
     for s in x.shape[axis + 1:]:
         inner *= s
     L = _lib.lib()
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         st = L.ib200_spline_coeff(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], outer, n, inner,
                                   int(bound), int(order), x.device.index, _lib.stream_ptr(x.device))
     _lib.check(st)

@@ -75,7 +75,9 @@ def _dense_grid(grid, dim):
     """The tiled kernels stage (B, *spatial, D) grids as dense array-of-structs tiles; a strided grid (e.g.
     component-major, the layout `disp.movedim(1, -1)` leaves behind) runs on the one-thread-per-point kernels,
     3-4x slower on large 3-D problems than paying one copy of the grid."""
-    if dim == 3 and grid.shape[0] > 0 and grid[0].numel() >= 3 * 32768 and not grid[0].is_contiguous():
+    if dim != 3 or grid.is_contiguous() or grid.shape[0] == 0:
+        return grid
+    if grid[0].numel() >= 3 * 32768 and not grid[0].is_contiguous():
         return grid.contiguous()
     return grid
 
@@ -138,7 +140,7 @@ def _gather(fn_name, inp, grid, bound, interpolation, extrapolate, trailing, gou
     _set_vol(p, inp, batch, dim)
     _set_grid(p, grid, batch, dim)
     L = _lib.lib()
-    with torch.cuda.device(grid.device):
+    with _lib.on_device(grid.device):
         s = _lib.stream_ptr(grid.device)
         if gout is None:
             out = torch.empty([batch, channels, *oshape, *trailing(dim)], dtype=dtype, device=grid.device)
@@ -176,7 +178,7 @@ def grid_pull_labels(inp, grid, bound: List[int], interpolation: List[int], extr
     _set_vol(p, inp, batch, dim)
     _set_grid(p, grid, batch, dim)
     L = _lib.lib()
-    with torch.cuda.device(grid.device):
+    with _lib.on_device(grid.device):
         out = torch.empty([batch, channels, *oshape], dtype=inp.dtype, device=grid.device)
         st = L.ib200_pull_labels(ctypes.byref(p), _lib.ptr(inp), _lib.ptr(grid), _lib.ptr(out), _lib.stream_ptr(grid.device))
     _lib.check(st)
@@ -243,7 +245,7 @@ def _scatter(fn_name, inp, grid, shape, bound, interpolation, extrapolate, comp=
     if inp is not None:
         _set_img(p, inp, batch, dim, comp)
     L = _lib.lib()
-    with torch.cuda.device(grid.device):
+    with _lib.on_device(grid.device):
         out = torch.empty([batch, channels, *shape], dtype=dtype, device=grid.device)
         nscratch = L.ib200_scratch_bytes(ctypes.byref(p))
         scratch = torch.empty([nscratch // 4], dtype=torch.float32, device=grid.device) if nscratch else None

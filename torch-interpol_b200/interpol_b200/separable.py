@@ -26,7 +26,7 @@ def _call(fn_name, x, coords, axis, n_out, bound, order, extrapolate, all_neares
     outer, inner = _geom(x, axis)
     out = torch.empty([*x.shape[:axis], n_out, *x.shape[axis + 1:]], dtype=x.dtype, device=x.device)
     L = _lib.lib()
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         st = getattr(L, fn_name)(_lib.ptr(x), _lib.ptr(out), _lib.ptr(coords), _lib.DTYPE_CODE[x.dtype],
                                  outer, x.shape[axis], n_out, inner, int(order), int(bound), int(extrapolate),
                                  int(bool(all_nearest)), int(bool(all_linear)), x.device.index,

@@ -213,3 +213,70 @@ def test_pipe_push_full_size_adjoint():
     ref = _with_flags(pp, NO_PIPE, lambda: pp.grid_count(grid, [256] * 3, [6], [3], 1))
     assert ib.last_kernel().startswith('count_tile3d')
     assert rel_err(to_np(cnt), to_np(ref)) <= 4e-6
+
+
+def _pipe_claimed():
+    import ctypes
+    from interpol_b200 import _lib
+    buf = (ctypes.c_int * 1)()
+    rc = _lib.lib().ib200_debug_pipe_control(buf)
+    return rc, buf[0]
+
+
+@pytest.mark.parametrize('op', ['pull', 'grad', 'bwd_grid'])
+@pytest.mark.parametrize('static', [False, True])
+def test_pipe_dynamic_tile_claims(op, static, monkeypatch):
+    """Tiles beyond the first of each CTA are claimed from a global counter (IB200_STATIC_TILES=1: the static
+    round-robin that streams under capture use): every tile must be processed exactly once either way."""
+    import oracle
+    import interpol_b200 as ib
+    from interpol_b200 import pushpull as pp
+    if static:
+        monkeypatch.setenv('IB200_STATIC_TILES', '1')
+    gen = torch.Generator().manual_seed(5 + static)
+    shape, vshape = (48, 40, 200), (48, 40, 232)
+    vol = torch.randn([2, 1, *vshape], generator=gen)
+    grid = smooth_grid(shape, gen, amp=2.0, batch=2)
+    grid[..., 2] = grid[..., 2] * 1.12 + 0.3
+    grid = grid.contiguous()
+    b, o = [3, 1, 3], [3]
+    if op == 'pull':
+        got = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_pull(vol.cuda(), grid.cuda(), b, o, 1))
+        want = oracle.grid_pull(vol.double().numpy(), grid.double().numpy(), b, o, 1)
+    elif op == 'grad':
+        got = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_grad(vol.cuda(), grid.cuda(), b, o, 1))
+        want = oracle.grid_grad(vol.double().numpy(), grid.double().numpy(), b, o, 1)
+    else:
+        gout = torch.randn([2, 1, *shape], generator=gen)
+        got = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_pull_grad_grid(gout.cuda(), vol.cuda(), grid.cuda(), b, o, 1))
+        want = oracle.grid_grad(vol.double().numpy(), grid.double().numpy(), b, o, 1)[:, 0] * gout.double().numpy()[:, 0, ..., None]
+    assert '_pipe3d' in ib.last_kernel(), ib.last_kernel()
+    rc, claimed = _pipe_claimed()
+    ntiles = 2 * (shape[0] // 8) * (shape[1] // 8) * ((shape[2] + 31) // 32)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    if static:
+        assert rc == -1
+    else:
+        assert rc == 0 and ntiles - sms <= claimed <= ntiles + sms, (claimed, ntiles)
+    assert rel_err(to_np(got), want) <= 1e-5
+
+
+def test_pipe_under_stream_capture_matches_eager():
+    """a captured launch takes the static schedule (no counter word baked into the graph)"""
+    from interpol_b200 import pushpull as pp
+    gen = torch.Generator().manual_seed(9)
+    shape = (48, 40, 96)
+    vol = torch.randn([1, 1, *shape], generator=gen).cuda()
+    grid = smooth_grid(shape, gen, amp=2.0).cuda()
+    eager = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_pull(vol, grid, [3], [3], 1))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _with_flags(pp, FORCE_PIPE, lambda: pp.grid_pull(vol, grid, [3], [3], 1))      # warm-up outside capture
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = _with_flags(pp, FORCE_PIPE, lambda: pp.grid_pull(vol, grid, [3], [3], 1))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)

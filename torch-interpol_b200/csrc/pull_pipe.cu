@@ -23,6 +23,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "pipe_common.cuh"
 
 namespace ib200 {
@@ -30,6 +33,7 @@ namespace ib200 {
 // Phase timers (clock64 ticks, accumulated in registers by the producer warp and consumer warp 0 of
 // CTA 0, written once at kernel exit) -- filled only when IB200_PIPE_DEBUG is set in the environment.
 __device__ long long g_pipe_dbg[16];
+__device__ long long g_pipe_cta[256 * 4];   // per CTA: start / end of consumer warp 0 (globaltimer ns), its loop ticks, its tiles
 // (compiled in with -DIB200_PIPE_TIMERS only -- IB200_TUNE builds, profiles/pipe_debug.py: the clock reads and
 // their predicated adds were ~30 instructions per warp and tile on the consumers' path)
 #if defined(IB200_TUNE) && !defined(IB200_PIPE_TIMERS)
@@ -45,6 +49,7 @@ __device__ long long g_pipe_dbg[16];
 
 constexpr int kNG = 4;     // ring of grid-coordinate tiles
 constexpr int kNB = 2;     // ring of boxes
+constexpr int kTileCtrSlots = 1024;
 
 template <int ORDER, int OP, int W>
 __device__ __noinline__ float3 pull_point_global(const KParams &kp, const float *src, float c0, float c1, float c2) {
@@ -81,11 +86,11 @@ __device__ __noinline__ float3 pull_point_global(const KParams &kp, const float 
 }
 
 template <int ORDER, int OP, int NCW>
-__global__ void __launch_bounds__(32 * (NCW + 1), 1)
+__global__ void __launch_bounds__(32 * (NCW + 2), 1)
 pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_grid, const float *__restrict__ vol,
                    const float *__restrict__ gout, float *__restrict__ out, const int ntiles, const int cmul, const int bmul, const int gbmul,
-                   const unsigned inv_ntz, const unsigned inv_nty, const unsigned inv_ntx, long long *dbg) {
+                   const unsigned inv_ntz, const unsigned inv_nty, const unsigned inv_ntx, int *tile_ctr, long long *dbg) {
     constexpr int TX = 8, TY = 8, TZ = 32;
     constexpr int NPT = TX * TY * TZ;
     constexpr int NROWS = TX * TY;
@@ -108,12 +113,13 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
     PipeGeom *planned = reinterpret_cast<PipeGeom *>(qkeys + 24);                       // [4] parts of the planned tile
     int *zoff = reinterpret_cast<int *>(planned + 4);                                   // [kNB][kZLut] folded z word of an unfolded index
     float *zsgn = reinterpret_cast<float *>(zoff + kNB * kZLut);                        // [kNB][kZLut] its sign
+    int *tile_ring = reinterpret_cast<int *>(zsgn + kNB * kZLut);                       // [kNG] tile held by a coordinate slot (-1: none left)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNG; ++i) { mbar_init(gfull + i, 1); mbar_init(gempty + i, NCW); }
         for (int i = 0; i < kNB; ++i) { mbar_init(bfull + i, 1); mbar_init(bempty + i, NCW); }
-        mbar_init(kfull, NCW); mbar_init(kfull + 1, NCW);
+        mbar_init(kfull, 1); mbar_init(kfull + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         tma_prefetch_desc(&tm_vol);
         tma_prefetch_desc(&tm_grid);
@@ -123,13 +129,17 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
 
     const int ntx = (kp.pts_n[0] + TX - 1) / TX, nty = (kp.pts_n[1] + TY - 1) / TY, ntz = (kp.pts_n[2] + TZ - 1) / TZ;
     const int C = (int)kp.channels;
-    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... (neighbouring CTAs work on neighbouring
-    // tiles at the same time, so halos are shared through L2)
-    const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    auto decode = [&](int q, int &b, int &x0, int &y0, int &z0) {
-        const int t = (int)blockIdx.x + q * (int)gridDim.x;
+    // Tiles are handed out in ascending order: the first one is blockIdx.x, every further one is claimed from a
+    // global counter by the producer when it requests the tile's coordinates (two tiles ahead of the taps), so
+    // a CTA that drew expensive tiles (stretched or boundary regions cost up to 2x) simply draws fewer of them
+    // -- with the static round-robin the slowest CTA ran 25 % longer than the average one.  Neighbouring CTAs
+    // still work on neighbouring tiles at the same time (halos shared through L2).  tile_ctr == nullptr (stream
+    // capture): static round-robin.  The tile of sequence number q travels with its coordinate slot
+    // (tile_ring[q % kNG], published by the gfull barrier); -1 ends the sequence for every role.
+    auto decode = [&](int t, int &b, int &x0, int &y0, int &z0, int &nzv) {
         const int t1 = fast_div(t, inv_ntz), t2 = fast_div(t1, inv_nty), t3 = fast_div(t2, inv_ntx);
         b = t3; x0 = (t2 - t3 * ntx) * TX; y0 = (t1 - t2 * nty) * TY; z0 = (t - t1 * ntz) * TZ;
+        nzv = min(TZ, kp.pts_n[2] - z0);
     };
 
     // Schedule.  The box of tile j is reduced by the consumers while they process tile j-2 (its
@@ -138,26 +148,49 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
     // the consumers' path ever waits for memory or for the (slow, single-warp) producer.
     if (warp == NCW) {
         // ================================ producer ================================
-        auto request_grid = [&](int q) {
-            int b, x0, y0, z0;
-            decode(q, b, x0, y0, z0);
+        bool ended = false;                          // the sentinel has been published
+        // claim(q): lane 0 draws the tile of sequence number q (the global atomic is issued early, its latency
+        // hides behind the planning of tile q - 2); publish(q, t): coordinates requested, tile id in the ring
+        auto claim = [&](int q) {
+            int t = -1;
+            if (lane == 0 && !ended) {
+                if (q == 0) t = (int)blockIdx.x;
+                else if (tile_ctr) t = (int)gridDim.x + atomicAdd(tile_ctr, 1);
+                else t = (int)blockIdx.x + q * (int)gridDim.x;
+                if (t >= ntiles) t = -1;
+            }
+            return t;
+        };
+        auto publish = [&](int q, int t) {
+            if (ended) return;
             const int s = q % kNG, u = q / kNG;
+            t = __shfl_sync(0xffffffffu, t, 0);
             if (u > 0) mbar_wait(gempty + s, (u - 1) & 1);
             if (lane == 0) {
-                mbar_expect_tx(gfull + s, NPT * 3 * 4);
-                tma_load_4d(gtile + (size_t)s * NPT * 3, &tm_grid, z0 * 3, y0, x0, b * gbmul, gfull + s);
+                tile_ring[s] = t;
+                if (t >= 0) {
+                    int b, x0, y0, z0, nzv;
+                    decode(t, b, x0, y0, z0, nzv);
+                    mbar_expect_tx(gfull + s, NPT * 3 * 4);
+                    tma_load_4d(gtile + (size_t)s * NPT * 3, &tm_grid, z0 * 3, y0, x0, b * gbmul, gfull + s);
+                }
                 mbar_arrive(gfull + s);
             }
+            __syncwarp();
+            ended = t < 0;
         };
-        if (my_tiles > 0) request_grid(0);
-        if (my_tiles > 1) request_grid(1);
+        publish(0, claim(0));
+        publish(1, claim(1));
         int n = 0;                                   // box sequence number
 #ifdef IB200_PIPE_TIMERS
         long long a_kfull = 0, a_plan = 0, a_grid = 0, a_bempty = 0, a_issue = 0;
 #endif
-        for (int j = 0; j < my_tiles; ++j) {
-            int b, x0, y0, z0;
-            decode(j, b, x0, y0, z0);
+        for (int j = 0;; ++j) {
+            const int t = tile_ring[j % kNG];        // written by lane 0 of this warp (request_grid ends with __syncwarp)
+            if (t < 0) break;
+            int b, x0, y0, z0, nzv;
+            decode(t, b, x0, y0, z0, nzv);
+            const int t_ahead = claim(j + 2);
             // ---- plan: whole tile, z halves or z quarters ----
             TICK(t_k);
             mbar_wait(kfull + (j & 1), (j >> 1) & 1);
@@ -170,7 +203,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                 if (g0.mode != PIPE_GLOBAL) {
                     if (lane == 0) planned[0] = g0;
                 } else {
-                    const int nxv = min(TX, kp.pts_n[0] - x0), nyv = min(TY, kp.pts_n[1] - y0), nzv = min(TZ, kp.pts_n[2] - z0);
+                    const int nxv = min(TX, kp.pts_n[0] - x0), nyv = min(TY, kp.pts_n[1] - y0);
                     pipe_quarter_boxes<TX, TY, TZ>(kp, gtile + (size_t)(j % kNG) * NPT * 3, nxv, nyv, nzv, qkeys);
                     g0 = pipe_geom<ORDER>(kp, qkeys, 0, 2);
                     const PipeGeom g1 = pipe_geom<ORDER>(kp, qkeys, 2, 4);
@@ -189,12 +222,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                 if (lane < 6) keys_base[(j & 1) * 8 + lane] = pipe_key_init(lane);      // ready for tile j + 2
                 __syncwarp();
             }
-            // coordinates of tile j + 2 (their buffer was released with tile j - 2).  Must precede the boxes:
-            // the consumers wait for them before they touch (and can release) the first part of tile j.
             TOCK(a_plan, t_p);
-            TICK(t_g);
-            if (j + 2 < my_tiles) request_grid(j + 2);
-            TOCK(a_grid, t_g);
             // ---- one box per (channel, part) ----
             for (int c = 0; c < C; ++c) {
                 for (int part = 0; part < nparts; ++part, ++n) {
@@ -228,45 +256,53 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     TOCK(a_issue, t_i);
                 }
             }
+            // coordinates of tile j + 2 (their buffer was released with tile j - 2, like the box just refilled):
+            // after the boxes, which are what the consumers are about to wait for
+            TICK(t_g);
+            publish(j + 2, t_ahead);
+            TOCK(a_grid, t_g);
         }
 #ifdef IB200_PIPE_TIMERS
         if (dbg && blockIdx.x == 0 && lane == 0) { dbg[0] = a_kfull; dbg[1] = a_plan; dbg[2] = a_grid; dbg[3] = a_bempty; dbg[4] = a_issue; }
 #endif
-    } else {
-        // ================================ consumers ===============================
-            const bool masked = kp.extrapolate != 1;
-        for (int q = 0; q < 2 && q < my_tiles; ++q) {      // boxes of the first two tiles, cooperatively
-            int b, x0, y0, z0;
-            decode(q, b, x0, y0, z0);
+    } else if (warp == NCW + 1) {
+        // ================================= scout ==================================
+        // reduces the bounding box of the support starts of every tile as soon as its coordinates have
+        // landed (two tiles ahead of the consumers), so the tap loop carries no look-ahead state
+        for (int q = 0;; ++q) {
             mbar_wait(gfull + q % kNG, (q / kNG) & 1);
-            pipe_tile_box<TX, TY, TZ, NCW>(kp, gtile + (size_t)(q % kNG) * NPT * 3, min(TX, kp.pts_n[0] - x0), min(TY, kp.pts_n[1] - y0),
-                                           min(TZ, kp.pts_n[2] - z0), keys_base + (q & 1) * 8, warp);
+            const int t = tile_ring[q % kNG];
+            if (t < 0) break;
+            int b, x0, y0, z0, nzv;
+            decode(t, b, x0, y0, z0, nzv);
+            pipe_tile_box<TX, TY, TZ, 1>(kp, gtile + (size_t)(q % kNG) * NPT * 3, min(TX, kp.pts_n[0] - x0), min(TY, kp.pts_n[1] - y0),
+                                         nzv, keys_base + (q & 1) * 8, 0);
             __syncwarp();
             if (lane == 0) mbar_arrive(kfull + (q & 1));
         }
+    } else {
+        // ================================ consumers ===============================
         int n = 0;
 #ifdef IB200_PIPE_TIMERS
         long long a_gfull = 0, a_bfull = 0, a_fix = 0, a_rows = 0, a_rel = 0, a_items = 0;
 #endif
         TICK(t_all);
-        for (int q = 0; q < my_tiles; ++q) {
-            int b, x0, y0, z0;
-            decode(q, b, x0, y0, z0);
-            const int nxv = min(TX, kp.pts_n[0] - x0), nyv = min(TY, kp.pts_n[1] - y0), nzv = min(TZ, kp.pts_n[2] - z0);
+#ifdef IB200_PIPE_TIMERS
+        long long gt0 = 0;
+        int ntl = 0;
+        if (dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+#endif
+        for (int q = 0;; ++q) {
+            mbar_wait(gfull + q % kNG, (q / kNG) & 1);      // landed long ago (the scout has been through it): acquire only
+            const int t = tile_ring[q % kNG];
+            if (t < 0) break;
+            int b, x0, y0, z0, nzv;
+            decode(t, b, x0, y0, z0, nzv);
+#ifdef IB200_PIPE_TIMERS
+            ++ntl;
+#endif
+            const int nxv = min(TX, kp.pts_n[0] - x0), nyv = min(TY, kp.pts_n[1] - y0);
             const float *gt = gtile + (size_t)(q % kNG) * NPT * 3;
-            // while the rows of tile q are evaluated, the box of tile q + 2 is reduced on the side
-            bool look = q + 2 < my_tiles;
-            int nxv2 = 0, nyv2 = 0, nzv2 = 0;
-            const float *gt2 = gtile + (size_t)((q + 2) % kNG) * NPT * 3 + lane * 3;
-            float mn[3] = {3e38f, 3e38f, 3e38f}, mx[3] = {-3e38f, -3e38f, -3e38f};
-            if (look) {
-                int b2, x2, y2, z2;
-                decode(q + 2, b2, x2, y2, z2);
-                nxv2 = min(TX, kp.pts_n[0] - x2); nyv2 = min(TY, kp.pts_n[1] - y2); nzv2 = min(TZ, kp.pts_n[2] - z2);
-                TICK(t_g);
-                mbar_wait(gfull + (q + 2) % kNG, ((q + 2) / kNG) & 1);
-                TOCK(a_gfull, t_g);
-            }
             for (int c = 0; c < C; ++c) {
                 const float *src = vol + (i64)b * kp.vol_sb + (i64)c * kp.vol_sc;
                 // lattice offset of this lane's voxel in row 0 of the tile (32-bit: pts_total * 3 < 2^31)
@@ -310,15 +346,6 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                         int rn = 0;
                         if (lane == 0) rn = atomicAdd(rowctr + s, 1);      // claimed early: its latency hides behind the taps
                         const int p = r / TY, ly = r - p * TY;
-                        if (look && p < nxv2 && ly < nyv2 && lane < nzv2) {
-                            const float c2[3] = {gt2[r * (TZ * 3)], gt2[r * (TZ * 3) + 1], gt2[r * (TZ * 3) + 2]};
-                            bool use = true;
-                            if (masked) use = inbounds<float, 3>(kp, c2);
-                            if (use) {
-#pragma unroll
-                                for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], c2[d]); mx[d] = fmaxf(mx[d], c2[d]); }
-                            }
-                        }
                         if (p < nxv && ly < nyv && lane_ok) {
                             const float *gp = gt + (r * TZ + lane) * 3;
                             const float cc[3] = {gp[0], gp[1], gp[2]};
@@ -431,13 +458,6 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     }
                     TOCK(a_rows, t_r);
                     TICK(t_e);
-                    if (look) {
-                        // every row of the tile has been claimed exactly once: the box of tile q + 2 is complete
-                        pipe_merge_box(mn, mx, keys_base + (q & 1) * 8);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(kfull + (q & 1));
-                        look = false;
-                    }
                     // ---- release the box (and, after the last part of the last channel, the coordinates) ----
                     if (g.mode == PIPE_FOLD) fence_async_smem();
                     __syncwarp();
@@ -454,6 +474,12 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
             }
         }
 #ifdef IB200_PIPE_TIMERS
+        if (dbg && warp == 0 && lane == 0 && blockIdx.x < 256) {
+            long long gt1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+            g_pipe_cta[blockIdx.x * 4] = gt0; g_pipe_cta[blockIdx.x * 4 + 1] = gt1;
+            g_pipe_cta[blockIdx.x * 4 + 2] = clock64() - t_all; g_pipe_cta[blockIdx.x * 4 + 3] = ntl;
+        }
         if (dbg && blockIdx.x == 0 && warp == 0 && lane == 0) {
             dbg[5] = a_gfull; dbg[6] = a_bfull; dbg[7] = a_fix; dbg[8] = a_rows; dbg[9] = a_rel; dbg[10] = a_items;
             dbg[11] = clock64() - t_all;
@@ -464,11 +490,45 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
 
 // ---------------------------------------------------------------- launch --
 
+// Tile counters of the dynamic schedule: one word per stream in flight (launches on one stream are ordered, so
+// they can share a word; it is zeroed in-stream before every launch).  A stream under capture gets none (static
+// round-robin): a captured node would carry its word into replays on other streams.
+__device__ int g_tile_ctr[kTileCtrSlots];
+
+static int *g_last_ctl = nullptr;    // counter of the last launch (debugging aid, ib200_debug_pipe_control)
+
+static int *pipe_control_for(cudaStream_t stream) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+    if (getenv("IB200_STATIC_TILES")) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, int> slots;
+    static std::map<int, int *> base;
+    std::lock_guard<std::mutex> lock(mu);
+    int *b = nullptr;
+    auto ib = base.find(dev);
+    if (ib == base.end()) {
+        if (cudaGetSymbolAddress((void **)&b, g_tile_ctr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        base[dev] = b;
+    } else b = ib->second;
+    auto key = std::make_pair(dev, stream);
+    auto it = slots.find(key);
+    if (it == slots.end()) {
+        if ((int)slots.size() >= kTileCtrSlots) return nullptr;      // more live streams than words: static schedule
+        it = slots.emplace(key, (int)slots.size()).first;
+    }
+    int *ctr = b + it->second;
+    if (cudaMemsetAsync(ctr, 0, sizeof(int), stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ctr;
+}
+
 template <int ORDER, int OP, int NCW>
 static int launch_pull_pipe(const KParams &kp, const float *vol, const float *grid, const float *gout, float *out, cudaStream_t stream) {
     constexpr int NPT = 8 * 8 * 32;
     const size_t smem_total = (size_t)kNB * kBoxWords * 4 + (size_t)kNG * NPT * 3 * 4 + kNB * sizeof(PipeGeom) +
-                              (2 * kNG + 2 * kNB + 2) * sizeof(unsigned long long) + (3 * kNB + 40) * sizeof(int) + 4 * sizeof(PipeGeom) + (size_t)kNB * kZLut * 8 + 64;
+                              (2 * kNG + 2 * kNB + 2) * sizeof(unsigned long long) + (3 * kNB + 40 + kNG) * sizeof(int) + 4 * sizeof(PipeGeom) + (size_t)kNB * kZLut * 8 + 64;
     const i64 ntiles = kp.batch * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
     if (ntiles == 0) return 1;
     if (ntiles * kp.channels > 0x3fffffffLL) return 0;
@@ -501,8 +561,10 @@ static int launch_pull_pipe(const KParams &kp, const float *vol, const float *gr
     const int nblocks = (int)(ntiles < pipe_sm_count() ? ntiles : pipe_sm_count());
     long long *dbg = nullptr;
     if (getenv("IB200_PIPE_DEBUG")) IB200_CUDA_CHECK(cudaGetSymbolAddress((void **)&dbg, g_pipe_dbg));
-    kern<<<nblocks, 32 * (NCW + 1), smem_total, stream>>>(kp, tm_vol, tm_grid, vol, gout, out, (int)ntiles, cmul, bmul, gbmul,
-        make_inv((kp.pts_n[2] + 31) / 32), make_inv((kp.pts_n[1] + 7) / 8), make_inv((kp.pts_n[0] + 7) / 8), dbg);
+    int *ctl = ntiles > nblocks ? pipe_control_for(stream) : nullptr;
+    g_last_ctl = ctl;
+    kern<<<nblocks, 32 * (NCW + 2), smem_total, stream>>>(kp, tm_vol, tm_grid, vol, gout, out, (int)ntiles, cmul, bmul, gbmul,
+        make_inv((kp.pts_n[2] + 31) / 32), make_inv((kp.pts_n[1] + 7) / 8), make_inv((kp.pts_n[0] + 7) / 8), ctl, dbg);
     static thread_local char name[64];
     snprintf(name, sizeof(name), "%s_pipe3d_o%d", OP == OP_GRAD ? "grad" : OP == OP_PULL_BWD_GRID ? "pullbwd" : "pull", ORDER);
     note_launch(name);
@@ -535,7 +597,7 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
     if (kp.pts_n[2] % 4 || kp.grid_sb % 4) return 0;
     const float *v = (const float *)vol, *g = (const float *)grid, *go = (const float *)gout_;
     float *o = (float *)out;
-    constexpr int NCW = 15;
+    constexpr int NCW = 14;
     if (op == OP_PULL) {
         switch (kp.order[0]) {
         case 1: return launch_pull_pipe<1, OP_PULL, NCW>(kp, v, g, nullptr, o, stream);
@@ -561,6 +623,16 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
 }  // namespace ib200
 
 // debugging aid (not part of the public ABI): phase timers of the last pipe launch
+// debugging aid (not part of the public ABI): tiles claimed from the counter by the last persistent pull / grad
+// launch (including the failed claim that ends every CTA); -1 when that launch had no counter.  Synchronises.
+extern "C" __attribute__((visibility("default"))) int ib200_debug_pipe_control(int *out1) {
+    if (!ib200::g_last_ctl) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    return cudaMemcpy(out1, ib200::g_last_ctl, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+extern "C" __attribute__((visibility("default"))) int ib200_debug_pipe_cta(long long *out1024) {
+    return cudaMemcpyFromSymbol(out1024, ib200::g_pipe_cta, sizeof(long long) * 1024) == cudaSuccess ? 0 : -1;
+}
 extern "C" __attribute__((visibility("default"))) int ib200_debug_pipe_counters(long long *out16) {
     return cudaMemcpyFromSymbol(out16, ib200::g_pipe_dbg, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
 }

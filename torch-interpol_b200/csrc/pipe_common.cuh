@@ -268,10 +268,14 @@ __device__ __forceinline__ void pipe_fixup_plane(const KParams &kp, const PipeGe
     const bool x_in = a >= g.r0[0] && a < g.r1[0];
     const int ax = x_in ? a : fx - g.lo[0];
     const bool x_src = x_in || (ax >= g.r0[0] && ax < g.r1[0]);
-    const bool z_all = g.r0[2] == 0 && g.r1[2] == vpr;
-    for (int bb = lane >> 1; bb < g.ext[1]; bb += 16) {
+    // (row, 4-word vector) items of the plane are dealt to the lanes round-robin: what needs rewriting is usually
+    // a few whole rows next to a face, and with one row per lane pair only a handful of lanes had any work
+    const int nitems = g.ext[1] * vpr;
+    for (int it = lane; it < nitems; it += 32) {
+        const int bb = it / vpr, v = it - bb * vpr;
         const bool y_in = bb >= g.r0[1] && bb < g.r1[1];
-        if (x_in && y_in && z_all) continue;
+        const bool v_in = v >= g.r0[2] && v < g.r1[2];
+        if (x_in && y_in && v_in) continue;
         const int sy = g.lo[1] + bb;
         // (axes of bound `zero` count as in range -- the TMA fill is their answer -- but their sign is 0 outside)
         const int fy = bound_index<int>(kp.bound[1], sy, kp.vol_n[1]);
@@ -281,23 +285,37 @@ __device__ __forceinline__ void pipe_fixup_plane(const KParams &kp, const PipeGe
         const float *brow = bx + ax * kBoxPlane + by * kBoxZ;
         const float *grow = src + fx * (int)kp.vol_s[0] + fy * (int)kp.vol_s[1];
         float *dstrow = bx + a * kBoxPlane + bb * kBoxZ;
-        for (int v = lane & 1; v < vpr; v += 2) {
-            const bool v_in = v >= g.r0[2] && v < g.r1[2];
-            if (x_in && y_in && v_in) continue;
-            float val[4];
+        float val[4];
+        // a folded-z box holds RAW volume words (the taps apply the z map, dst1's zero at voxel 0 included)
+        const int nzvol = kp.vol_n[2], sz0 = g.lo[2] + 4 * v;
+        const bool z_inside = sz0 >= 0 && sz0 + 3 <= nzvol - 1;
+        int vec = 0;            // 1: signed copy of a vector of the box, 2: of the volume (16-byte aligned: lo[2] % 4 == 0)
+        int gz0 = sz0;
+        if (xy_src && v_in && (!g.zfold || sz0 + 3 <= nzvol - 1)) vec = 1;      // a row / plane mirrored at an x / y face
+        else if (!xy_src && z_inside && (g.zfold || kp.bound[2] != IB200_BOUND_DST1)) vec = 2;   // its source lies outside the box
+        else if (!g.zfold && !z_inside && kp.bound[2] == IB200_BOUND_DFT && (nzvol & 3) == 0 && nzvol >= 4) {
+            gz0 = bound_index<int>(IB200_BOUND_DFT, sz0, nzvol);                  // wraps as a whole: nz % 4 == 0
+            vec = 2;
+        }
+        if (sgxy == 0) {
+            val[0] = 0.f; val[1] = 0.f; val[2] = 0.f; val[3] = 0.f;              // (nothing is read: the folded indices may mean nothing)
+        } else if (vec != 0) {
+            const float4 t = vec == 1 ? *reinterpret_cast<const float4 *>(brow + 4 * v) : __ldg(reinterpret_cast<const float4 *>(grow + gz0));
+            const float sg = (float)sgxy;
+            val[0] = sg * t.x; val[1] = sg * t.y; val[2] = sg * t.z; val[3] = sg * t.w;
+        } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int sz = g.lo[2] + 4 * v + k;
-                // a folded-z box holds RAW volume words (the taps apply the z map, dst1's zero at voxel 0 included)
-                const int fz = g.zfold ? min(sz, kp.vol_n[2] - 1) : bound_index<int>(kp.bound[2], sz, kp.vol_n[2]);
-                const int sg = g.zfold ? sgxy : sgxy * bound_sign<int>(kp.bound[2], sz, kp.vol_n[2]);
+                const int sz = sz0 + k;
+                const int fz = g.zfold ? min(sz, nzvol - 1) : bound_index<int>(kp.bound[2], sz, nzvol);
+                const int sg = g.zfold ? sgxy : sgxy * bound_sign<int>(kp.bound[2], sz, nzvol);
                 const int zz = fz - g.lo[2];
                 float t = 0.f;
                 if (sg != 0) t = (xy_src && zz >= 4 * g.r0[2] && zz < 4 * g.r1[2]) ? brow[zz] : __ldg(grow + fz);
                 val[k] = (float)sg * t;
             }
-            *reinterpret_cast<float4 *>(dstrow + 4 * v) = make_float4(val[0], val[1], val[2], val[3]);
         }
+        *reinterpret_cast<float4 *>(dstrow + 4 * v) = make_float4(val[0], val[1], val[2], val[3]);
     }
 }
 

@@ -302,6 +302,7 @@ def cpu_step_fn(spec, slab, inputs=None):
                     o = ref.grid_pull(v, g, **kw)
                     o.backward(torch.ones_like(o))
                     out[op] = g.grad
+                    out['pull_backward_input'] = v.grad
             return out
         return fn, 'reference', torch.get_num_threads(), sample + '; reference TorchScript path', nvox
     import oracle
@@ -621,6 +622,14 @@ def parity_vs_cpu(spec, vol, grid, cpu_fn, slab):
             img = got['pull'] if 'pull' in got else v0[:, :, :slab].contiguous()
             got[o] = pp.grid_push(img, g0, list(v0.shape[2:]), [BOUND_CODES[b] for b in spec['bound']], [spec['order']],
                                   1 if spec['extrapolate'] else 0)
+        elif o == 'pull_backward':
+            # the CPU arm back-propagates ones through grid_pull: same cotangent here (the timed steps use randn)
+            ones = torch.ones([1, v0.shape[1], *g0.shape[1:-1]], device=v0.device, dtype=v0.dtype)
+            gi, gg = pp.grid_pull_backward(ones, v0.clone().requires_grad_(), g0.clone().requires_grad_(),
+                                           [BOUND_CODES[b] for b in spec['bound']], [spec['order']], 1 if spec['extrapolate'] else 0)
+            got[o] = gg
+            if 'pull_backward_input' in cpu:
+                got['pull_backward_input'] = gi
     worst, per = 0.0, {}
     for o, g in got.items():
         ref = cpu[o]

@@ -105,8 +105,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(geoms + kNB);
     unsigned long long *gfull = bars, *gempty = bars + kNG, *bfull = bars + 2 * kNG, *bempty = bars + 2 * kNG + kNB;
     unsigned long long *kfull = bars + 2 * kNG + 2 * kNB;                               // [2] box of a tile reduced
-    int *rowctr = reinterpret_cast<int *>(bars + 2 * kNG + 2 * kNB + 2);                // [kNB] next unclaimed z-row
-    int *fixctr = rowctr + kNB;                                                         // [kNB] next unclaimed fix-up plane
+    int *fixctr = reinterpret_cast<int *>(bars + 2 * kNG + 2 * kNB + 2) + kNB;                                                                 // [kNB] next unclaimed fix-up plane
     int *fixdone = fixctr + kNB;                                                        // [kNB] fixed planes
     int *keys_base = fixdone + kNB;                                                      // [2][6] boxes of tiles j, j+1 (+2 pad each)
     int *qkeys = keys_base + 16;                                                        // [24] quarter boxes (rare)
@@ -234,7 +233,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     TICK(t_i);
                     if (lane == 0) {
                         geoms[s] = g;
-                        rowctr[s] = 0; fixctr[s] = 0; fixdone[s] = 0;
+                        fixctr[s] = 0; fixdone[s] = 0;
                     }
                     if (g.zfold) {
                         for (int e = lane; e < g.zn; e += 32) {
@@ -337,14 +336,14 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                     }
                     TOCK(a_fix, t_f);
                     TICK(t_r);
-                    // ---- taps: z-rows of the tile are claimed dynamically (a slow warp never holds the box) ----
+                    // ---- taps ----
                     const bool lane_ok = lane < nzv && lane >= g.zlo && lane < g.zhi;
-                    int r = 0;
-                    if (lane == 0) r = atomicAdd(rowctr + s, 1);
-                    r = __shfl_sync(0xffffffffu, r, 0);
+                    // z-rows are dealt statically, rotated from box to box so that the warps that get the extra
+                    // row (NROWS % NCW of them) change every time: claiming rows from a shared counter (round 1)
+                    // balanced perfectly but cost an ATOMS round trip and a SHFL per row -- measured 5 % slower (profiles/r2zi)
+                    int r = (warp + (n % NCW) * (NCW - NROWS % NCW)) % NCW;
                     while (r < NROWS) {
-                        int rn = 0;
-                        if (lane == 0) rn = atomicAdd(rowctr + s, 1);      // claimed early: its latency hides behind the taps
+                        const int rn = r + NCW;
                         const int p = r / TY, ly = r - p * TY;
                         if (p < nxv && ly < nyv && lane_ok) {
                             const float *gp = gt + (r * TZ + lane) * 3;
@@ -454,7 +453,7 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                             if (!GRAD) dst[o] = res[0];
                             else { dst[o * 3] = res[0]; dst[o * 3 + 1] = res[1]; dst[o * 3 + 2] = res[2]; }
                         }
-                        r = __shfl_sync(0xffffffffu, rn, 0);
+                        r = rn;
                     }
                     TOCK(a_rows, t_r);
                     TICK(t_e);
@@ -597,7 +596,7 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
     if (kp.pts_n[2] % 4 || kp.grid_sb % 4) return 0;
     const float *v = (const float *)vol, *g = (const float *)grid, *go = (const float *)gout_;
     float *o = (float *)out;
-    constexpr int NCW = 14;
+    constexpr int NCW = 14;     // (16 warps of 4 rows each need <= 96 registers: measured 4 % slower, profiles/r2zj)
     if (op == OP_PULL) {
         switch (kp.order[0]) {
         case 1: return launch_pull_pipe<1, OP_PULL, NCW>(kp, v, g, nullptr, o, stream);

@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_C', 'libinterpol_b200.so')
+# (IB200_LIB: another build of the same library, e.g. a variant compiled for an A/B measurement under profiles/)
+LIB_PATH = os.environ.get('IB200_LIB') or os.path.join(_HERE, '_C', 'libinterpol_b200.so')
 
 F16, F32, F64, BF16 = 0, 1, 2, 3
 DTYPE_CODE = {torch.float16: F16, torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}

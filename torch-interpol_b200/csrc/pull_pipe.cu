@@ -581,13 +581,15 @@ int try_pull_pipe(int op, const KParams &kp, int dtype, const void *vol, const v
     if (kp.pts_total < 32768) return 0;
     if (kp.pts_total * 3 > 0x7fffffffLL) return 0;
     if (kp.flags & (IB200_FLAG_REF_LINEAR_GRAD_SIGN | IB200_FLAG_NO_PIPE | IB200_FLAG_DISPLACEMENT)) return 0;   // (displacement fields: tile kernel)
-    // The pipeline needs a dozen tiles per CTA to amortise its ramp-up (128^3: 7 per CTA, 0.20 ms against
-    // 0.10 ms for the one-tile-per-CTA kernel), and with several channels the tile kernel, which shares one
-    // plan and one staged grid tile between the channels of a tile, is still 3-7 % ahead (256^3 C=4: pull 1.13
-    // vs 1.17 ms, grad 1.34 vs 1.44 ms).  IB200_FLAG_FORCE_PIPE overrides (tests, profiling).
+    // The pipeline needs a dozen or two tiles per CTA to amortise its ramp-up and its three-tile tail
+    // (profiles/r2zl, benchmark deformation: 160^3 = 13.5 tiles per SM, cubic 0.195 ms against 0.138 ms for the
+    // one-tile-per-CTA kernel, linear 0.058 against 0.065; 192^3 = 23 per SM: 0.151 / 0.170 and 0.077 / 0.106), and
+    // with several channels the tile kernel, which shares one plan and one staged grid tile between the channels
+    // of a tile, is still ahead (256^3 C=4: pull 1.05 vs 1.17 ms).  IB200_FLAG_FORCE_PIPE overrides (tests, profiling).
     if (!(kp.flags & IB200_FLAG_FORCE_PIPE)) {
         const i64 tiles = kp.batch * ((kp.pts_n[0] + 7) / 8) * ((kp.pts_n[1] + 7) / 8) * ((kp.pts_n[2] + 31) / 32);
-        if (tiles < 12 * (i64)pipe_sm_count() || kp.channels > 1) return 0;
+        const i64 per_sm = kp.order[0] == 1 ? 10 : 18;
+        if (tiles < per_sm * (i64)pipe_sm_count() || kp.channels > 1) return 0;
     }
     // TMA: unit innermost stride, 16-byte aligned bases and strides
     if (kp.vol_s[2] != 1) return 0;

@@ -2,19 +2,25 @@
 // float32 storage): the tiled gather of pull_tile.cu restructured so that the tap
 // loop never waits for memory.
 //
-//   grid = one CTA per SM, each looping over tiles of 8 x 8 x 32 output voxels.
-//   warp 0 (producer)
-//     - streams the grid coordinates of tiles n+1, n+2 into a 3-deep ring, one TMA
-//       tile copy (cp.async.bulk.tensor, box 8 x 8 x 96 floats) per tile;
-//     - reduces the bounding box of all spline supports of tile n (REDUX);
+//   grid = one CTA per SM, each looping over tiles of 8 x 8 x 32 output voxels; tiles beyond a CTA's first
+//   are claimed from a global counter (a CTA that draws expensive tiles draws fewer).
+//   warps 0 .. NCW-1 (consumers)
+//     - wait on the box's mbarrier, (rarely) fix up folded elements, then evaluate
+//       (ORDER+1)^3 LDS taps per voxel and store the result; rows are 64 words so
+//       that the bank of a tap depends on z only; the 64 z-rows of a tile are dealt to
+//       the warps statically, rotated from box to box.
+//   warp NCW (producer)
+//     - claims tiles two ahead of the taps and streams their grid coordinates into a
+//       4-deep ring, one TMA tile copy (cp.async.bulk.tensor, box 8 x 8 x 96 floats) per tile;
+//     - turns the bounding box of a tile (from the scout) into a plan: whole tile, z halves or
+//       z quarters, plain / folded box, or the global fallback;
 //     - issues one TMA tile copy per x-plane of the box of the input volume (box
 //       16 rows x 64 words) into a 2-deep ring of boxes; the TMA unit zero-fills
 //       whatever lies outside the volume, which IS the `zero` boundary condition;
 //       for the other bounds a fix-up pass rewrites the out-of-volume elements.
-//   warps 1.. (consumers)
-//     - wait on the box's mbarrier, (rarely) fix up folded elements, then evaluate
-//       (ORDER+1)^3 LDS taps per voxel and store the result; rows are 64 words so
-//       that the bank of a tap depends on z only.
+//   warp NCW+1 (scout)
+//     - reduces the bounding box of all spline supports of every tile as soon as its
+//       coordinates have landed (REDUX + shared atomics).
 //   Boxes that do not fit (incoherent deformation) are gathered from global
 //   memory by the consumers with identical arithmetic.
 //
@@ -97,7 +103,6 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
     constexpr int W = ORDER + 1;
     constexpr bool GRAD = (OP == OP_GRAD || OP == OP_PULL_BWD_GRID);
     constexpr bool BWD = (OP == OP_PULL_BWD_GRID);     // fused backward w.r.t. the grid: grad * gout (one channel)
-    constexpr int NCT = NCW * 32;                  // consumer threads
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *box = reinterpret_cast<float *>(smem_raw);                                   // [kNB][kBoxWords]
     float *gtile = box + (size_t)kNB * kBoxWords;                                       // [kNG][NPT * 3]

@@ -104,6 +104,20 @@ def test_no_cpu_fallback():
         ib.spline_coeff_nd(x, interpolation=3)
 
 
+def test_missing_library_fails_loudly(tmp_path):
+    """IB200_LIB points the loader at another build (A/B measurements); a path without a library must raise,
+    not fall back to anything (checked in a fresh interpreter: the loader caches its handle)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from interpol_b200 import _lib\n"
+            "try:\n    _lib.lib()\nexcept _lib.ExtensionMissing as e:\n    print('missing:', e)\n" % os.path.join(root, 'torch-interpol_b200'))
+    env = dict(os.environ, IB200_LIB=str(tmp_path / 'nowhere.so'))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+    assert 'missing:' in out.stdout and 'nowhere.so' in out.stdout, out.stdout + out.stderr
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, 'torch-interpol_b200')
     for base, _, files in os.walk(pkg):

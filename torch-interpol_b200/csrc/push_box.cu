@@ -370,27 +370,32 @@ push_box3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ CU
                     next_requested = true;
                 }
                 // ---- c. flush the box: fixed -> float, fold + sign, global REDs -------------
-                const int nrows = g.ext[0] * g.ext[1];
-                const int total = nrows * g.vpr;
+                // (the geometry lives on the stack -- its arrays are indexed in loops elsewhere -- and the flush loop
+                // used to re-read seven of its words from local memory per vector: copies in registers)
+                const int g_vpr = g.vpr, g_e1 = g.ext[1], g_e2 = g.ext[2], g_ps = g.ps, g_hs = g.hs;
+                const int g_lo0 = g.lo[0], g_lo1 = g.lo[1], g_lo2 = g.lo[2];
+                const bool g_plain = g.plain != 0;
+                const int vs0 = (int)kp.vol_s[0], vs1 = (int)kp.vol_s[1], vs2 = (int)kp.vol_s[2], nz1 = kp.vol_n[2] - 1;
+                const int total = g.ext[0] * g_e1 * g_vpr;
                 const int zlo = (kp.bound[2] == IB200_BOUND_DST1) ? 1 : 0;
                 const unsigned inv_vpr = g.inv_vpr, inv_e1 = g.inv_e1;
                 for (int q = threadIdx.x; q < total; q += NT) {
-                    const int rr = fast_div(q, inv_vpr), v4 = q - rr * g.vpr;
-                    const int a = fast_div(rr, inv_e1), bb = rr - a * g.ext[1];
-                    const int4 iv = *reinterpret_cast<const int4 *>(acc + a * g.ps + (bb >> 1) * kBoxRow + (bb & 1) * g.hs + v4 * 4);
+                    const int rr = fast_div(q, inv_vpr), v4 = q - rr * g_vpr;
+                    const int a = fast_div(rr, inv_e1), bb = rr - a * g_e1;
+                    const int4 iv = *reinterpret_cast<const int4 *>(acc + a * g_ps + (bb >> 1) * kBoxRow + (bb & 1) * g_hs + v4 * 4);
                     if ((iv.x | iv.y | iv.z | iv.w) == 0) continue;
                     float rowsgn = 1.f;
                     int rowbase;
-                    if (g.plain) {
-                        rowbase = (g.lo[0] + a) * (int)kp.vol_s[0] + (g.lo[1] + bb) * (int)kp.vol_s[1];
+                    if (g_plain) {
+                        rowbase = (g_lo0 + a) * vs0 + (g_lo1 + bb) * vs1;
                     } else {
                         rowsgn = sgn_tab[a] * sgn_tab[kBoxMaxExt + bb];
                         if (rowsgn == 0.f) continue;
                         rowbase = idx_tab[a] + idx_tab[kBoxMaxExt + bb];
                     }
                     const float f = inv * rowsgn;
-                    const int zs = g.lo[2] + v4 * 4;
-                    if (vec_ok && zs >= zlo && zs + 3 <= kp.vol_n[2] - 1) {
+                    const int zs = g_lo2 + v4 * 4;
+                    if (vec_ok && zs >= zlo && zs + 3 <= nz1) {
                         atomicAdd(reinterpret_cast<float4 *>(dst + rowbase + zs),
                                   make_float4(f * (float)iv.x, f * (float)iv.y, f * (float)iv.z, f * (float)iv.w));
                     } else {
@@ -398,9 +403,9 @@ push_box3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ CU
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int ee = v4 * 4 + e;
-                            if (ivs[e] != 0 && ee < g.ext[2]) {
-                                const float sg = g.plain ? 1.f : sgn_tab[2 * kBoxMaxExt + ee];
-                                const int zi = g.plain ? (g.lo[2] + ee) * (int)kp.vol_s[2] : idx_tab[2 * kBoxMaxExt + ee];
+                            if (ivs[e] != 0 && ee < g_e2) {
+                                const float sg = g_plain ? 1.f : sgn_tab[2 * kBoxMaxExt + ee];
+                                const int zi = g_plain ? (g_lo2 + ee) * vs2 : idx_tab[2 * kBoxMaxExt + ee];
                                 if (sg != 0.f) atomicAdd(dst + rowbase + zi, f * sg * (float)ivs[e]);
                             }
                         }

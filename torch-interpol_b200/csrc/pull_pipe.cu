@@ -53,6 +53,10 @@ __device__ long long g_pipe_cta[256 * 4];   // per CTA: start / end of consumer 
 #define TOCK(acc, var) do { } while (0)
 #endif
 
+__device__ __forceinline__ void st_global(float *p, float v) {
+    asm volatile("st.global.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
+}
+
 constexpr int kNG = 4;     // ring of grid-coordinate tiles
 constexpr int kNB = 2;     // ring of boxes
 constexpr int kTileCtrSlots = 1024;
@@ -313,7 +317,11 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                 const int o0 = (x0 * kp.pts_n[1] + y0) * kp.pts_n[2] + z0 + lane;
                 float *dst = out + ((i64)b * kp.channels + c) * kp.pts_total * (GRAD ? 3 : 1) + (GRAD ? 3 * o0 : o0);
                 const float *gm = BWD ? gout + (i64)b * kp.img_sb + (i64)c * kp.img_sc + o0 : nullptr;
-                const int ostride_y = kp.pts_n[2], ostride_x = kp.pts_n[1] * kp.pts_n[2];
+                int ostride_y = kp.pts_n[2], ostride_x = kp.pts_n[1] * kp.pts_n[2];
+                // kept in registers: the compiler otherwise re-reads them from the constant bank on every row's store
+                // path and the shared-window base through S2R at every row start (2-3 % of the stall samples each)
+                unsigned gt_s = smem_u32(gt);
+                asm volatile("" : "+r"(ostride_y), "+r"(ostride_x), "+r"(gt_s), "+l"(dst));
                 bool last;
                 do {
                     const int s = n % kNB;
@@ -351,8 +359,12 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                         const int rn = r + NCW;
                         const int p = r / TY, ly = r - p * TY;
                         if (p < nxv && ly < nyv && lane_ok) {
-                            const float *gp = gt + (r * TZ + lane) * 3;
-                            const float cc[3] = {gp[0], gp[1], gp[2]};
+                            float cc[3];
+                            {
+                                const unsigned ga = gt_s + (unsigned)((r * TZ + lane) * 12);
+                                asm volatile("ld.shared.f32 %0, [%3];\n\tld.shared.f32 %1, [%3+4];\n\tld.shared.f32 %2, [%3+8];\n"
+                                             : "=f"(cc[0]), "=f"(cc[1]), "=f"(cc[2]) : "r"(ga));
+                            }
                             float res[3] = {0.f, 0.f, 0.f};
                             if (g.mode == PIPE_GLOBAL) {
                                 const float3 r3 = pull_point_global<ORDER, OP, W>(kp, src, cc[0], cc[1], cc[2]);
@@ -455,8 +467,9 @@ pull_pipe3d_kernel(const __grid_constant__ KParams kp, const __grid_constant__ C
                             }
                             const int o = p * ostride_x + ly * ostride_y;
                             if (BWD) { const float m = gm[o]; res[0] *= m; res[1] *= m; res[2] *= m; }
-                            if (!GRAD) dst[o] = res[0];
-                            else { dst[o * 3] = res[0]; dst[o * 3 + 1] = res[1]; dst[o * 3 + 2] = res[2]; }
+                            // (explicit global stores: `dst` went through an opaque register copy above)
+                            if (!GRAD) st_global(dst + o, res[0]);
+                            else { st_global(dst + o * 3, res[0]); st_global(dst + o * 3 + 1, res[1]); st_global(dst + o * 3 + 2, res[2]); }
                         }
                         r = rn;
                     }
